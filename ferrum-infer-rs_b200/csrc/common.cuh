@@ -1,0 +1,142 @@
+// common.cuh -- shared declarations of libfb2_w4a16.so (host + device).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/fb2_w4a16.h"
+
+namespace fb2 {
+
+// ----------------------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define FB2_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      fb2::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                     __LINE__);                                                         \
+      return FB2_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define FB2_LAUNCH_CHECK()                                                              \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      fb2::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),        \
+                     __FILE__, __LINE__);                                               \
+      return FB2_ERR_CUDA;                                                              \
+    }                                                                                   \
+    fb2::count_launch();                                                                \
+  } while (0)
+
+// ------------------------------------------------------------------ tiled weight format
+// The "tile stripe" layout the tensor-core kernels stream (data layout):
+//   for each 128-column tile t, for each 128-row group g (rows in act-order-SORTED k):
+//     8192 B  packed int4: 4 chunks of 32 k; chunk c = 128 rows(n) x uint4; word j of the
+//             uint4 holds k = 32c + 8j + {0,2,4,6,1,3,5,7} in nibbles 0..7
+//      512 B  128 x u32: lo half = f16 scale, hi half = f16 (1024 + zero)
+constexpr int kTileN = 128;          // weight columns per tile  (UMMA M)
+constexpr int kGroup = 128;          // k rows per stage == GPTQ group_size of the fast path
+constexpr int kChunkK = 32;          // k per uint4
+constexpr int kStageWBytes = kTileN * kGroup / 2;           // 8192
+constexpr int kStageSZBytes = kTileN * 4;                   // 512
+constexpr int kStageBytes = kStageWBytes + kStageSZBytes;   // 8704
+
+// ------------------------------------------------------------------------ row-block map
+// Every GEMM kernel works on "row blocks": up to NB activation rows that share one weight
+// matrix (one expert).  Three sources describe them.
+enum RowMode : int { ROWS_DENSE = 0, ROWS_DISPATCH = 1, ROWS_ROUTED = 2 };
+
+struct DispatchEntry {  // one (expert, in_row, out_row, m) of gemm_phase_batched, <= NB rows
+  int expert, in_row, out_row, m;
+};
+// Dispatch entries travel BY VALUE in the kernel parameter block (graph-capturable, no
+// H2D copy); longer lists are launched in chunks.
+constexpr int kMaxDispatchBlocks = 240;
+struct DispatchTable {
+  DispatchEntry e[kMaxDispatchBlocks];
+};
+
+struct RowMap {
+  int mode;
+  int m;                             // DENSE: number of rows
+  // ROUTED (moe_align_block_size outputs)
+  const int32_t *sorted_ids;         // [capacity]
+  const int32_t *block_experts;      // [capacity / block]
+  const int32_t *num_post_padded;    // [1]
+  int block;                         // moe_block_size
+  int top_k;
+  int num_valid;                     // prob_m * top_k: ids >= this are padding
+  // DISPATCH: entries come from the DispatchTable kernel parameter
+  int num_dispatch;
+  int max_blocks;                    // host-side upper bound of the number of row blocks
+};
+
+// Weight descriptor shared by all kernels (dense linear, expert view, or stack).
+struct WeightRef {
+  // tiled format (fast path); null when the layer only has the raw format
+  const uint8_t *tiles;              // [experts][n_tiles_total][groups][kStageBytes]
+  const int32_t *perm;               // [K] sorted position -> disk row, or null
+  // raw format (generic path)
+  const int32_t *qweight;            // [experts][K/8][ld]
+  const __half *scales;              // [experts][G][ld]
+  const int32_t *qzeros;             // [experts][G][ld/8]
+  const int32_t *g_idx;              // [K] or null
+  const float *bias;                 // [n] or null (dense / expert view only)
+  int k, n;                          // logical GEMM K and N of one expert (or view)
+  int ld;                            // columns per expert in storage (>= col0 + n)
+  int col0;                          // first column of the view inside the expert
+  int group_size;
+  int num_experts;
+};
+
+// ---------------------------------------------------------------------- kernel launchers
+// generic_kernels.cu
+int launch_generic_gemm(const WeightRef &w, const RowMap &rows, const __half *x, __half *y,
+                        int epilogue /*0 none, 1 silu_mul*/, cudaStream_t stream);
+int launch_generic_gemm_dispatch(const WeightRef &w, const RowMap &rows, const DispatchTable &tbl,
+                                 const __half *x, __half *y, cudaStream_t stream);
+int launch_dequant(const WeightRef &w, int expert, float *out_f32, __half *out_f16,
+                   cudaStream_t stream);
+int launch_permute_cols(const __half *x, const int32_t *perm, __half *xp, int m, int k,
+                        cudaStream_t stream);
+int launch_silu_mul_split(const __half *gu, __half *out, size_t tokens, size_t im, int gelu,
+                          cudaStream_t stream);
+// moe_kernels.cu
+int launch_route_topk_softmax(const __half *logits, int32_t *ids, float *wts, int batch,
+                              int num_experts, int top_k, int norm, cudaStream_t stream);
+int launch_build_pairs(const int32_t *expert_ids, int32_t *pairs_by_token,
+                       int32_t *packed_token_idx, int32_t *expert_offsets, int pairs,
+                       int num_experts, int top_k, cudaStream_t stream);
+int launch_align_block_size(const int32_t *expert_ids, int32_t *sorted_ids, int32_t *block_ids,
+                            int32_t *total_post_pad, int pairs, int num_experts, int block_size,
+                            int sorted_max, int pair_ids, cudaStream_t stream);
+int launch_moe_combine(const __half *packed_down, const int32_t *pairs_by_token,
+                       const float *weights, __half *out, int batch, int hidden, int top_k,
+                       cudaStream_t stream);
+// tc_gemm.cu
+struct TcScratch {
+  float *partials;                   // split-K partial sums
+  size_t partial_bytes;
+  int32_t *counters;                 // self-resetting tile arrival counters
+  size_t num_counters;
+};
+bool tc_supported(const WeightRef &w);
+// Bytes of split-K partial scratch a forward with up to max_rows rows may need.
+size_t tc_partial_bytes(const WeightRef &w, size_t max_rows);
+size_t tc_num_counters(const WeightRef &w, size_t max_rows);
+int launch_tc_gemm(const WeightRef &w, const RowMap &rows, int max_blocks, const __half *x,
+                   __half *y, int epilogue, const TcScratch &scratch, int sm_count,
+                   cudaStream_t stream);
+const char *tc_kernel_name(const WeightRef &w, size_t m);
+
+}  // namespace fb2

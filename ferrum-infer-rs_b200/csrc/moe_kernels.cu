@@ -1,0 +1,271 @@
+// moe_kernels.cu -- MoE routing and post-op kernels (BackendMoeFused surface).
+//
+// Semantics follow the reference kernels; the implementations are new:
+//   router        crates/ferrum-kernels/kernels/moe_router.cu:32        (expf instead of __expf so
+//                 the result tracks the host router, ferrum-models/src/moe/router.rs:113-195)
+//   build_pairs   crates/ferrum-kernels/kernels/moe_build_pairs.cu:24
+//   align         crates/ferrum-kernels/kernels/moe_align_block_size.cu:46, _pair_ids.cu:13
+//   combine       crates/ferrum-kernels/kernels/moe_combine.cu:29,62
+// The reference sorts with shared-memory atomics in ONE block, so the order of pairs
+// inside an expert's run depends on scheduling.  Here one CTA per expert ranks its pairs
+// with an ordered block scan: the output is deterministic (ascending pair id, the order
+// the host plan MoeBucketPlan::rebuild_into produces, moe/dispatch.rs:1408-1461) and the
+// sort scales over SMs instead of one.
+#include "common.cuh"
+
+namespace fb2 {
+namespace {
+
+constexpr int kSortThreads = 256;
+constexpr int kMaxExperts = 1024;
+
+// Ordered rank of this thread's matches inside the block.  Returns the exclusive prefix of
+// `mine` over threads and the block total.
+__device__ __forceinline__ int block_exclusive_scan(int mine, int *smem_warp, int &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int v = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) smem_warp[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    int wv = lane < (int)(blockDim.x >> 5) ? smem_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wv, o);
+      if (lane >= o) wv += t;
+    }
+    smem_warp[32 + lane] = wv;  // inclusive over warps
+  }
+  __syncthreads();
+  const int warp_base = warp ? smem_warp[32 + warp - 1] : 0;
+  total = smem_warp[32 + (blockDim.x >> 5) - 1];
+  __syncthreads();
+  return warp_base + v - mine;
+}
+
+__global__ void __launch_bounds__(32)
+router_kernel(const __half *__restrict__ logits, int32_t *__restrict__ out_ids,
+              float *__restrict__ out_w, int batch, int num_experts, int top_k, int norm) {
+  extern __shared__ float probs[];
+  const int row = blockIdx.x, lane = threadIdx.x;
+  if (row >= batch) return;
+  float tmax = -INFINITY;
+  for (int i = lane; i < num_experts; i += 32) {
+    float v = __half2float(logits[(size_t)row * num_experts + i]);
+    probs[i] = v;
+    tmax = v > tmax ? v : tmax;
+  }
+  for (int o = 16; o; o >>= 1) {
+    float t = __shfl_xor_sync(0xffffffffu, tmax, o);
+    tmax = t > tmax ? t : tmax;
+  }
+  __syncwarp();
+  // The host router sums exp() left to right in one f32 accumulator (router.rs:150-155);
+  // lane 0 does the same so that the normaliser is the same number.
+  float sum = 0.f;
+  for (int i = lane; i < num_experts; i += 32) probs[i] = expf(probs[i] - tmax);
+  __syncwarp();
+  if (lane == 0)
+    for (int i = 0; i < num_experts; i++) sum += probs[i];
+  sum = __shfl_sync(0xffffffffu, sum, 0);
+  const float inv = 1.0f / sum;
+  for (int i = lane; i < num_experts; i += 32) probs[i] *= inv;
+  __syncwarp();
+
+  float sel_sum = 0.f;
+  for (int k = 0; k < top_k; k++) {
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+    for (int i = lane; i < num_experts; i += 32) {
+      float v = probs[i];
+      if (v > best) { best = v; best_i = i; }
+    }
+    // max value, ties -> smaller index
+    for (int o = 16; o; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (best_i == 0x7fffffff) best_i = 0;  // all -inf: reference keeps best_idx = 0
+    if (lane == 0) {
+      out_ids[(size_t)row * top_k + k] = best_i;
+      out_w[(size_t)row * top_k + k] = best;
+      probs[best_i] = -INFINITY;
+    }
+    sel_sum += best;
+    __syncwarp();
+  }
+  if (norm && lane < top_k) {
+    // K <= 32 handled by one pass; larger K loops
+    for (int k = lane; k < top_k; k += 32) {
+      if (sel_sum > 0.f) out_w[(size_t)row * top_k + k] *= (1.0f / sel_sum);
+      else out_w[(size_t)row * top_k + k] = 1.0f / (float)top_k;
+    }
+  }
+}
+
+// grid = num_experts CTAs.  CTA e ranks the pairs routed to expert e.
+__global__ void __launch_bounds__(kSortThreads)
+build_pairs_kernel(const int32_t *__restrict__ expert_ids, int32_t *__restrict__ pairs_by_token,
+                   int32_t *__restrict__ packed_token_idx, int32_t *__restrict__ expert_offsets,
+                   int pairs, int num_experts, int top_k) {
+  __shared__ int warp_sums[64];
+  const int e = blockIdx.x;
+  const int per = (pairs + kSortThreads - 1) / kSortThreads;
+  const int p0 = min(pairs, (int)threadIdx.x * per), p1 = min(pairs, p0 + per);
+  int lt = 0, eq = 0;
+  for (int p = p0; p < p1; p++) {
+    int id = expert_ids[p];
+    bool valid = id >= 0 && id < num_experts;
+    lt += (valid && id < e);
+    eq += (valid && id == e);
+    if (e == 0 && !valid) pairs_by_token[p] = -1;
+  }
+  int total_lt, total_eq;
+  block_exclusive_scan(lt, warp_sums, total_lt);
+  int my_base = block_exclusive_scan(eq, warp_sums, total_eq);
+  if (threadIdx.x == 0) {
+    expert_offsets[e] = total_lt;
+    if (e == num_experts - 1) expert_offsets[num_experts] = total_lt + total_eq;
+  }
+  int slot = total_lt + my_base;
+  for (int p = p0; p < p1; p++) {
+    if (expert_ids[p] == e) {
+      pairs_by_token[p] = slot;
+      packed_token_idx[slot] = p / top_k;
+      slot++;
+    }
+  }
+}
+
+// grid = num_experts CTAs.  Every CTA builds the full histogram (cheap: pairs ints from L2)
+// so it can place its own expert's padded run without a second launch.
+__global__ void __launch_bounds__(kSortThreads)
+align_block_size_kernel(const int32_t *__restrict__ expert_ids,
+                        int32_t *__restrict__ sorted_ids, int32_t *__restrict__ block_ids,
+                        int32_t *__restrict__ total_post_pad, int pairs, int num_experts,
+                        int block_size, int sorted_max, int pair_ids) {
+  __shared__ int hist[kMaxExperts];
+  __shared__ int warp_sums[64];
+  __shared__ int s_pad_off, s_unpad_off, s_total_pad;
+  const int e = blockIdx.x;
+  for (int i = threadIdx.x; i < num_experts; i += kSortThreads) hist[i] = 0;
+  __syncthreads();
+  const int per = (pairs + kSortThreads - 1) / kSortThreads;
+  const int p0 = min(pairs, (int)threadIdx.x * per), p1 = min(pairs, p0 + per);
+  int eq = 0;
+  for (int p = p0; p < p1; p++) {
+    int id = expert_ids[p];
+    if (id >= 0 && id < num_experts) {
+      atomicAdd(&hist[id], 1);  // counts only: order-independent
+      eq += (id == e);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int pad = 0, unpad = 0, tot = 0;
+    for (int i = 0; i < num_experts; i++) {
+      int padded = ((hist[i] + block_size - 1) / block_size) * block_size;
+      if (i < e) { pad += padded; unpad += hist[i]; }
+      tot += padded;
+    }
+    s_pad_off = pad; s_unpad_off = unpad; s_total_pad = tot;
+  }
+  __syncthreads();
+  int total_eq;
+  int my_base = block_exclusive_scan(eq, warp_sums, total_eq);
+  const int pad_off = s_pad_off, unpad_off = s_unpad_off, total_pad = s_total_pad;
+  const int padded_e = ((total_eq + block_size - 1) / block_size) * block_size;
+  int rank = my_base;
+  for (int p = p0; p < p1; p++) {
+    if (expert_ids[p] == e) {
+      int slot = pad_off + rank;
+      if (slot < sorted_max) sorted_ids[slot] = pair_ids ? p : unpad_off + rank;
+      rank++;
+    }
+  }
+  // padding slots of this expert's run -> sentinel
+  for (int i = total_eq + threadIdx.x; i < padded_e; i += kSortThreads)
+    if (pad_off + i < sorted_max) sorted_ids[pad_off + i] = pairs;
+  for (int b = threadIdx.x; b < padded_e / block_size; b += kSortThreads)
+    block_ids[pad_off / block_size + b] = e;
+  if (e == num_experts - 1) {
+    for (int i = total_pad + threadIdx.x; i < sorted_max; i += kSortThreads) sorted_ids[i] = pairs;
+    if (threadIdx.x == 0) total_post_pad[0] = total_pad;
+  }
+}
+
+template <bool kPairs>
+__global__ void combine_kernel(const __half *__restrict__ rows, const int32_t *__restrict__ pairs_by_token,
+                               const float *__restrict__ weights, __half *__restrict__ out,
+                               int batch, int hidden, int top_k) {
+  const int b = blockIdx.y;
+  const int h2 = blockIdx.x * blockDim.x + threadIdx.x;   // pair of columns
+  if (b >= batch || h2 * 2 >= hidden) return;
+  float a0 = 0.f, a1 = 0.f;
+  for (int k = 0; k < top_k; k++) {
+    int row = kPairs ? pairs_by_token[b * top_k + k] : b * top_k + k;
+    if (row < 0) continue;
+    float w = weights[b * top_k + k];
+    __half2 v = *reinterpret_cast<const __half2 *>(rows + (size_t)row * hidden + h2 * 2);
+    a0 += w * __low2float(v);
+    a1 += w * __high2float(v);
+  }
+  *reinterpret_cast<__half2 *>(out + (size_t)b * hidden + h2 * 2) =
+      __halves2half2(__float2half_rn(a0), __float2half_rn(a1));
+}
+
+}  // namespace
+
+int launch_route_topk_softmax(const __half *logits, int32_t *ids, float *wts, int batch,
+                              int num_experts, int top_k, int norm, cudaStream_t stream) {
+  if (batch <= 0) return FB2_OK;
+  router_kernel<<<batch, 32, (size_t)num_experts * sizeof(float), stream>>>(
+      logits, ids, wts, batch, num_experts, top_k, norm);
+  FB2_LAUNCH_CHECK();
+  return FB2_OK;
+}
+
+int launch_build_pairs(const int32_t *expert_ids, int32_t *pairs_by_token,
+                       int32_t *packed_token_idx, int32_t *expert_offsets, int pairs,
+                       int num_experts, int top_k, cudaStream_t stream) {
+  build_pairs_kernel<<<num_experts, kSortThreads, 0, stream>>>(
+      expert_ids, pairs_by_token, packed_token_idx, expert_offsets, pairs, num_experts, top_k);
+  FB2_LAUNCH_CHECK();
+  return FB2_OK;
+}
+
+int launch_align_block_size(const int32_t *expert_ids, int32_t *sorted_ids, int32_t *block_ids,
+                            int32_t *total_post_pad, int pairs, int num_experts, int block_size,
+                            int sorted_max, int pair_ids, cudaStream_t stream) {
+  if (num_experts > kMaxExperts) {
+    set_error("moe_align_block_size: num_experts %d > %d", num_experts, kMaxExperts);
+    return FB2_ERR_UNSUPPORTED;
+  }
+  align_block_size_kernel<<<num_experts, kSortThreads, 0, stream>>>(
+      expert_ids, sorted_ids, block_ids, total_post_pad, pairs, num_experts, block_size,
+      sorted_max, pair_ids);
+  FB2_LAUNCH_CHECK();
+  return FB2_OK;
+}
+
+int launch_moe_combine(const __half *packed_down, const int32_t *pairs_by_token,
+                       const float *weights, __half *out, int batch, int hidden, int top_k,
+                       cudaStream_t stream) {
+  if (batch <= 0) return FB2_OK;
+  dim3 grid((hidden / 2 + 127) / 128, batch);
+  if (pairs_by_token)
+    combine_kernel<true><<<grid, 128, 0, stream>>>(packed_down, pairs_by_token, weights, out, batch,
+                                                   hidden, top_k);
+  else
+    combine_kernel<false><<<grid, 128, 0, stream>>>(packed_down, nullptr, weights, out, batch,
+                                                    hidden, top_k);
+  FB2_LAUNCH_CHECK();
+  return FB2_OK;
+}
+
+}  // namespace fb2

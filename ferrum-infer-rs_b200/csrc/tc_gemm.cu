@@ -1,0 +1,562 @@
+// tc_gemm.cu -- the sm_100a tensor-core W4A16 kernels (tcgen05 / TMEM / bulk-TMA).
+//
+// Formulation ("swapped operands"): y^T[n, m] = sum_k W[n, k] * x[m, k].  The 128 weight
+// columns of a tile sit on the UMMA M side, the activation rows on the UMMA N side
+// (N = 16 / 32 / 64), so a decode batch of 1..64 rows needs no padding to a 128-row MMA
+// tile, and the GPTQ packing (8 consecutive k of ONE column per 32-bit word) is already
+// the K-major order the A operand wants.
+//
+// Per CTA (one weight tile x one k-range x one row block):
+//   warp 0      bulk-TMA producer: streams 8704-byte stages (one 128x128 int4 group tile +
+//               its 128 scale/zero pairs, contiguous in HBM) into a 5-deep smem ring,
+//               completion on mbarriers (cp.async.bulk, L2 evict-first).
+//   warps 2-9   dequant: LDS.128 packed words -> lop3 magic-number int4->fp16, exact
+//               (q - zero) then one fp16 multiply by the scale [ == f16_rn of the CPU
+//               reference's f32 weight ] -> tcgen05.st into a 3-slot TMEM ring as the UMMA
+//               A operand.  Weights never go back to shared memory.
+//   warp 1      one elected thread issues tcgen05.mma (kind::f16, M=128, N=NB, K=16, A from
+//               TMEM, B = activations from shared memory, 128B-swizzled K-major),
+//               accumulating in TMEM; tcgen05.commit releases TMEM slots.
+//   warps 2-9   epilogue: tcgen05.ld the fp32 accumulator, then either store fp16 (+bias,
+//               or SiLU(gate)*up for gate||up expert tiles) or, with split-K, write an fp32
+//               partial; the LAST CTA to arrive on a tile (self-resetting counter) reduces
+//               the partials in split order -- deterministic, no lock workspace to zero.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "rowmap.cuh"
+
+namespace fb2 {
+
+namespace {
+
+constexpr int kStages = 5;            // smem ring depth (stages of kStageBytes)
+constexpr int kASlots = 3;            // TMEM A-operand ring (slots of one 128-k group)
+constexpr int kTmemCols = 256;        // allocation: [0,64) accumulators, [64,256) A ring
+constexpr int kTmemABase = 64;
+constexpr int kDequantWarps = 8;
+constexpr int kThreads = 64 + kDequantWarps * 32;   // 320
+constexpr int kXBytesMax = 64 * 1024;               // activation slice held in smem
+
+struct TcParams {
+  WeightRef w;
+  RowMap rm;
+  const __half *x;
+  __half *y;
+  float *partials;
+  int32_t *counters;
+  int n_tiles;            // output tiles per row block (N/128, or I/128 with the SiLU epilogue)
+  int splits;             // split-K factor
+  int gps;                // 128-k groups per split
+  int groups;             // K / 128
+  int tiles_per_expert;   // ld / 128
+  int ld_out;             // output row stride
+};
+
+__device__ __forceinline__ float silu_mul(float g, float u) { return (g / (1.0f + expf(-g))) * u; }
+
+struct SmemLayout {
+  uint32_t x, ring, bars, misc, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int nb, int gps) {
+  SmemLayout L;
+  L.x = 0;
+  uint32_t xbytes = (uint32_t)gps * 2u * (uint32_t)nb * 128u;
+  L.ring = (xbytes + 1023u) & ~1023u;
+  L.bars = L.ring + kStages * kStageBytes;          // 8-byte aligned (8704 % 8 == 0)
+  L.misc = L.bars + 32 * 8;
+  L.total = L.misc + 16 + 2 * 64 * 4 + 16;
+  return L;
+}
+
+// barrier indices
+enum { BAR_FULL_W = 0, BAR_EMPTY_W = kStages, BAR_FULL_A = 2 * kStages,
+       BAR_EMPTY_A = 2 * kStages + 2 * kASlots, BAR_X = 2 * kStages + 4 * kASlots,
+       BAR_ACC = BAR_X + 1, BAR_COUNT = BAR_ACC + 1 };
+static_assert(BAR_COUNT <= 32, "barrier area too small");
+
+// Dequantise one packed word (nibble p holds k offset {0,2,4,6,1,3,5,7}[p]) into 4 half2
+// registers (k0,k1) (k2,k3) (k4,k5) (k6,k7).
+__device__ __forceinline__ void dequant_word(uint32_t q, __half2 zlo, __half2 zhi, __half2 s2,
+                                             uint32_t *out) {
+  const uint32_t kMagic = 0x64006400u;                 // half2(1024, 1024)
+  const __half2 k16th = __float2half2_rn(0.0625f);
+  uint32_t lo0 = ptx::lop3_and_or(q, 0x000f000fu, kMagic);   // 1024 + q      (k0,k1)
+  uint32_t hi0 = ptx::lop3_and_or(q, 0x00f000f0u, kMagic);   // 1024 + 16 q   (k2,k3)
+  uint32_t q2 = q >> 8;
+  uint32_t lo1 = ptx::lop3_and_or(q2, 0x000f000fu, kMagic);  //               (k4,k5)
+  uint32_t hi1 = ptx::lop3_and_or(q2, 0x00f000f0u, kMagic);  //               (k6,k7)
+  __half2 v0 = __hsub2(*reinterpret_cast<__half2 *>(&lo0), zlo);          // q - z, exact
+  __half2 v1 = __hfma2(*reinterpret_cast<__half2 *>(&hi0), k16th, zhi);   // q - z, exact
+  __half2 v2 = __hsub2(*reinterpret_cast<__half2 *>(&lo1), zlo);
+  __half2 v3 = __hfma2(*reinterpret_cast<__half2 *>(&hi1), k16th, zhi);
+  v0 = __hmul2(v0, s2);  // one rounding: == f16_rn((q - z) * s)
+  v1 = __hmul2(v1, s2);
+  v2 = __hmul2(v2, s2);
+  v3 = __hmul2(v3, s2);
+  out[0] = *reinterpret_cast<uint32_t *>(&v0);
+  out[1] = *reinterpret_cast<uint32_t *>(&v1);
+  out[2] = *reinterpret_cast<uint32_t *>(&v2);
+  out[3] = *reinterpret_cast<uint32_t *>(&v3);
+}
+
+template <int NB>
+__device__ __forceinline__ void load_acc(uint32_t taddr, float *v) {
+  // NB/2 consecutive fp32 columns of this thread's lane
+  if constexpr (NB == 16) {
+    uint32_t r[8];
+    ptx::tmem_ld_x8(taddr, r);
+    ptx::tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < NB / 32; c++) {
+      uint32_t r[16];
+      ptx::tmem_ld_x16(taddr + c * 16, r);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; i++) v[c * 16 + i] = __uint_as_float(r[i]);
+    }
+  }
+}
+
+template <int NB, bool kSilu>
+__device__ __forceinline__ void tc_decode_body(const TcParams &p, const DispatchTable *tbl) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NACC = kSilu ? 2 : 1;
+  constexpr int HALF = NB / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / p.splits, split = blockIdx.x - tile * p.splits;
+  const int blk = blockIdx.y;
+  if (blk >= rowmap_num_blocks(p.rm, NB)) return;     // CTA-uniform, before any barrier
+
+  const int g0 = split * p.gps;
+  const int ng = min(p.groups, g0 + p.gps) - g0;
+  const int total_it = NACC * ng;
+  const int expert = rowmap_block_expert(p.rm, tbl, blk);
+
+  const SmemLayout L = smem_layout(NB, p.gps);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t bars = smem_base + L.bars;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + L.misc);
+  int *s_flag = reinterpret_cast<int *>(smem + L.misc + 4);
+  int *s_arow = reinterpret_cast<int *>(smem + L.misc + 16);
+  int *s_crow = s_arow + 64;
+
+  // ------------------------------------------------------------------ one-time setup
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kStages; i++) {
+        ptx::mbar_init(bar(BAR_FULL_W + i), 1);
+        ptx::mbar_init(bar(BAR_EMPTY_W + i), kDequantWarps);
+      }
+      for (int i = 0; i < 2 * kASlots; i++) {
+        ptx::mbar_init(bar(BAR_FULL_A + i), 4);
+        ptx::mbar_init(bar(BAR_EMPTY_A + i), 1);
+      }
+      ptx::mbar_init(bar(BAR_X), kDequantWarps);
+      ptx::mbar_init(bar(BAR_ACC), 1);
+      ptx::mbar_fence_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(s_tmem));
+  } else if (warp >= 2) {
+    const int t2 = threadIdx.x - 64;
+    if (t2 < NB) {
+      int ar = 0, cr = 0;
+      bool ok = rowmap_resolve(p.rm, tbl, NB, blk, t2, ar, cr);
+      s_arow[t2] = ok ? ar : -1;
+      s_crow[t2] = ok ? cr : -1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  // first weight tile of this CTA's output tile; with the SiLU epilogue the "up" tile sits
+  // n_tiles tiles further (gate || up along N)
+  const size_t tile_stride = (size_t)p.groups * kStageBytes;
+  const uint8_t *wtile0 =
+      p.w.tiles + ((size_t)expert * p.tiles_per_expert + p.w.col0 / kTileN + tile) * tile_stride +
+      (size_t)g0 * kStageBytes;
+
+  if (warp == 0) {
+    // =============================================================== bulk-TMA producer
+    if (lane == 0) {
+      const uint64_t pol = ptx::policy_evict_first();
+      for (int it = 0; it < total_it; it++) {
+        const int acc = it / ng, gi = it - acc * ng;
+        const int st = it % kStages;
+        ptx::mbar_wait(bar(BAR_EMPTY_W + st), ((it / kStages) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(bar(BAR_FULL_W + st), kStageBytes);
+        const uint8_t *src = wtile0 + (size_t)acc * p.n_tiles * tile_stride + (size_t)gi * kStageBytes;
+        ptx::bulk_g2s_hint(smem_base + L.ring + st * kStageBytes, src, kStageBytes,
+                           bar(BAR_FULL_W + st), pol);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ==================================================================== MMA issuer
+    constexpr uint32_t idesc = ptx::umma_idesc_f16(128, NB);
+    ptx::mbar_wait(bar(BAR_X), 0);
+    for (int it = 0; it < total_it; it++) {
+      const int acc = it / ng, gi = it - acc * ng;
+      const int slot = it % kASlots;
+      const uint32_t par = (it / kASlots) & 1;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        ptx::mbar_wait(bar(BAR_FULL_A + slot * 2 + h), par);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t xatom = smem_base + L.x + (uint32_t)(gi * 2 + h) * (NB * 128);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            const uint32_t a_t = tmem_base + kTmemABase + slot * 64 + h * 32 + kk * 8;
+            const uint64_t b_d = ptx::umma_desc_kmajor_sw128(xatom + kk * 32);
+            ptx::umma_f16_ts(tmem_base + acc * NB, a_t, b_d, idesc,
+                             (gi | h | kk) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(bar(BAR_EMPTY_A + slot * 2 + h));
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) ptx::tc_commit(bar(BAR_ACC));
+    __syncwarp();
+  } else {
+    // ============================================= activation load, dequant, epilogue
+    const int dw = warp - 2;              // 0..7
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int h = dw >> 2;                // which 64-k half of every group this warp owns
+    const int nl = q * 32 + lane;         // weight column inside the tile == TMEM lane
+    const int t2 = threadIdx.x - 64;      // 0..255
+
+    // ---- activations -> shared memory, UMMA K-major 128B-swizzled atoms of [NB x 64]
+    {
+      const int cpr = ng * 16;            // 16-byte chunks per row (8 halves each)
+      const int total = NB * cpr;
+      const __half *xk = p.x + (size_t)g0 * kGroup;
+      for (int idx = t2; idx < total; idx += kDequantWarps * 32) {
+        const int i = idx / cpr, c8 = idx - i * cpr;
+        const int ar = s_arow[i];
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (ar >= 0) v = *reinterpret_cast<const uint4 *>(xk + (size_t)ar * p.w.k + c8 * 8);
+        const uint32_t off = (uint32_t)(c8 >> 3) * (NB * 128) + (uint32_t)i * 128 +
+                             (uint32_t)(((c8 & 7) ^ (i & 7)) << 4);
+        *reinterpret_cast<uint4 *>(smem + L.x + off) = v;
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(BAR_X));
+    }
+
+    // ---- dequant loop
+    for (int it = 0; it < total_it; it++) {
+      const int st = it % kStages;
+      const int slot = it % kASlots;
+      ptx::mbar_wait(bar(BAR_FULL_W + st), (it / kStages) & 1);
+      const uint8_t *stage = smem + L.ring + st * kStageBytes;
+      const uint32_t sz = reinterpret_cast<const uint32_t *>(stage + kStageWBytes)[nl];
+      const uint4 w0 = *reinterpret_cast<const uint4 *>(stage + (size_t)(2 * h) * 2048 + nl * 16);
+      const uint4 w1 = *reinterpret_cast<const uint4 *>(stage + (size_t)(2 * h + 1) * 2048 + nl * 16);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(BAR_EMPTY_W + st));   // stage is in registers now
+
+      const __half s = __ushort_as_half((unsigned short)(sz & 0xFFFF));
+      const __half zl = __ushort_as_half((unsigned short)(sz >> 16));   // 1024 + z
+      const __half2 s2 = __half2half2(s);
+      const __half2 zlo = __half2half2(zl);
+      const __half2 zhi = __hsub2(__float2half2_rn(960.0f), zlo);       // -(64 + z), exact
+
+      uint32_t r0[16], r1[16];
+      dequant_word(w0.x, zlo, zhi, s2, r0 + 0);
+      dequant_word(w0.y, zlo, zhi, s2, r0 + 4);
+      dequant_word(w0.z, zlo, zhi, s2, r0 + 8);
+      dequant_word(w0.w, zlo, zhi, s2, r0 + 12);
+      dequant_word(w1.x, zlo, zhi, s2, r1 + 0);
+      dequant_word(w1.y, zlo, zhi, s2, r1 + 4);
+      dequant_word(w1.z, zlo, zhi, s2, r1 + 8);
+      dequant_word(w1.w, zlo, zhi, s2, r1 + 12);
+
+      ptx::mbar_wait(bar(BAR_EMPTY_A + slot * 2 + h), ((it / kASlots) & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kTmemABase + slot * 64 + h * 32;
+      ptx::tmem_st_x16(ta, r0);
+      ptx::tmem_st_x16(ta + 16, r1);
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(BAR_FULL_A + slot * 2 + h));
+    }
+
+    // ---- epilogue: this thread owns output column nl, activation rows [h*HALF, +HALF)
+    ptx::mbar_wait(bar(BAR_ACC), 0);
+    ptx::tc_fence_after();
+    float v[NACC][HALF];
+#pragma unroll
+    for (int a = 0; a < NACC; a++)
+      load_acc<NB>(tmem_base + ((uint32_t)(q * 32) << 16) + a * NB + h * HALF, v[a]);
+
+    const int col = tile * kTileN + nl;
+    if (p.splits == 1) {
+      const float bias = (!kSilu && p.w.bias) ? p.w.bias[col] : 0.0f;
+#pragma unroll
+      for (int j = 0; j < HALF; j++) {
+        const int cr = s_crow[h * HALF + j];
+        if (cr < 0) continue;
+        float o = kSilu ? silu_mul(v[0][j], v[NACC - 1][j]) : v[0][j] + bias;
+        p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
+      }
+    } else {
+      // split-K: fp32 partials, last arriver reduces in split order (deterministic)
+      const size_t tile_id = (size_t)blk * p.n_tiles + tile;
+      float *part = p.partials + (tile_id * p.splits + split) * (size_t)(NACC * NB * kTileN);
+#pragma unroll
+      for (int a = 0; a < NACC; a++)
+#pragma unroll
+        for (int j = 0; j < HALF; j++)
+          part[(size_t)(a * NB + h * HALF + j) * kTileN + nl] = v[a][j];
+      __threadfence();
+      ptx::named_bar_sync(1, kDequantWarps * 32);
+      if (t2 == 0) {
+        const int old = atomicAdd(p.counters + tile_id, 1);
+        *s_flag = (old == p.splits - 1);
+        if (old == p.splits - 1) p.counters[tile_id] = 0;   // self-reset for the next launch
+      }
+      ptx::named_bar_sync(1, kDequantWarps * 32);
+      if (*s_flag) {
+        __threadfence();
+        const float *base = p.partials + tile_id * p.splits * (size_t)(NACC * NB * kTileN);
+        const float bias = (!kSilu && p.w.bias) ? p.w.bias[col] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < HALF; j++) {
+          const int cr = s_crow[h * HALF + j];
+          if (cr < 0) continue;
+          float sum[NACC];
+#pragma unroll
+          for (int a = 0; a < NACC; a++) sum[a] = 0.0f;
+          for (int s = 0; s < p.splits; s++)
+#pragma unroll
+            for (int a = 0; a < NACC; a++)
+              sum[a] += __ldcg(base + (size_t)s * (NACC * NB * kTileN) +
+                               (size_t)(a * NB + h * HALF + j) * kTileN + nl);
+          float o = kSilu ? silu_mul(sum[0], sum[NACC - 1]) : sum[0] + bias;
+          p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
+        }
+      }
+    }
+  }
+
+  // -------------------------------------------------------------------------- teardown
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+template <int NB, bool kSilu>
+__global__ void __launch_bounds__(kThreads, 2) tc_decode_kernel(const TcParams p) {
+  tc_decode_body<NB, kSilu>(p, nullptr);
+}
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 2)
+tc_decode_dispatch_kernel(const TcParams p, const __grid_constant__ DispatchTable tbl) {
+  tc_decode_body<NB, false>(p, &tbl);
+}
+
+// ------------------------------------------------------------------------ host planning
+struct TcPlan {
+  int nb, row_blocks, n_tiles, splits, gps, nacc;
+  size_t partial_floats, counters;
+  uint32_t smem;
+};
+
+int pick_nb(int rows_per_block) { return rows_per_block <= 16 ? 16 : rows_per_block <= 32 ? 32 : 64; }
+
+TcPlan make_plan(const WeightRef &w, int nb, int row_blocks, int epilogue, int sm_count) {
+  TcPlan pl{};
+  pl.nb = nb;
+  pl.row_blocks = row_blocks;
+  pl.nacc = epilogue ? 2 : 1;
+  pl.n_tiles = (epilogue ? w.n / 2 : w.n) / kTileN;
+  const int groups = w.k / kGroup;
+  const int gps_cap = kXBytesMax / (nb * 256);            // activation slice must fit
+  const int s_min = (groups + gps_cap - 1) / gps_cap;
+  const long tiles = (long)pl.n_tiles * row_blocks;
+  const long slots = 2L * (sm_count > 0 ? sm_count : 148);
+  // cost model in units of one stage time: waves * (stages per CTA + fixed overhead)
+  double best = 1e30;
+  int best_s = s_min;
+  for (int s = s_min; s <= groups; s++) {
+    const int gps = (groups + s - 1) / s;
+    const int s_eff = (groups + gps - 1) / gps;
+    if (s_eff != s) continue;
+    const long ctas = tiles * s;
+    const long waves = (ctas + slots - 1) / slots;
+    const double cost = (double)waves * (gps * pl.nacc + 3.0) + (s > 1 ? 0.5 + 0.05 * s : 0.0);
+    if (cost < best - 1e-9) { best = cost; best_s = s; }
+    if (ctas >= 8 * slots) break;
+  }
+  pl.splits = best_s;
+  pl.gps = (groups + best_s - 1) / best_s;
+  pl.partial_floats = pl.splits > 1 ? (size_t)tiles * pl.splits * pl.nacc * nb * kTileN : 0;
+  pl.counters = pl.splits > 1 ? (size_t)tiles : 0;
+  pl.smem = smem_layout(nb, pl.gps).total;
+  return pl;
+}
+
+template <typename K>
+int set_smem(K kernel, uint32_t bytes) {
+  FB2_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return FB2_OK;
+}
+
+}  // namespace
+
+bool tc_supported(const WeightRef &w) {
+  return w.tiles != nullptr && w.group_size == kGroup && w.k % kGroup == 0 && w.n % kTileN == 0 &&
+         w.col0 % kTileN == 0 && w.ld % kTileN == 0;
+}
+
+const char *tc_kernel_name(const WeightRef &w, size_t m) {
+  (void)m;
+  return tc_supported(w) ? "tc-decode" : "generic";
+}
+
+static void plan_rows(const RowMap &rows, int max_blocks, int &nb, int &row_blocks) {
+  if (rows.mode == ROWS_DENSE) {
+    nb = pick_nb(rows.m);
+    row_blocks = (rows.m + nb - 1) / nb;
+  } else if (rows.mode == ROWS_DISPATCH) {
+    nb = rows.block;           // host pre-split the entries into chunks of <= rows.block rows
+    row_blocks = rows.num_dispatch;
+  } else {
+    nb = pick_nb(rows.block);
+    row_blocks = max_blocks;
+  }
+}
+
+size_t tc_partial_bytes(const WeightRef &w, size_t max_rows) {
+  // worst case over the row-block sizes a forward with <= max_rows rows can pick
+  size_t worst = 0;
+  for (int nb : {16, 32, 64}) {
+    const int rb = (int)((max_rows + nb - 1) / nb);
+    for (int epi = 0; epi < 2; epi++) {
+      if (epi && (w.n / 2) % kTileN) continue;
+      TcPlan pl = make_plan(w, nb, rb > 0 ? rb : 1, epi, 148);
+      worst = worst > pl.partial_floats * 4 ? worst : pl.partial_floats * 4;
+    }
+  }
+  return worst;
+}
+
+size_t tc_num_counters(const WeightRef &w, size_t max_rows) {
+  const size_t rb = (max_rows + 15) / 16;
+  return (size_t)(w.n / kTileN) * (rb > 0 ? rb : 1);
+}
+
+int launch_tc_gemm(const WeightRef &w, const RowMap &rows, int max_blocks, const __half *x,
+                   __half *y, int epilogue, const TcScratch &scratch, int sm_count,
+                   cudaStream_t stream) {
+  if (!tc_supported(w)) {
+    set_error("tensor-core path needs the tiled weight format (K,N multiples of 128, group 128)");
+    return FB2_ERR_UNSUPPORTED;
+  }
+  int nb, row_blocks;
+  plan_rows(rows, max_blocks, nb, row_blocks);
+  if (row_blocks <= 0) return FB2_OK;
+  if (epilogue && (w.n / 2) % kTileN) {
+    set_error("SiLU epilogue needs n_per_expert/2 to be a multiple of 128");
+    return FB2_ERR_SHAPE;
+  }
+  TcPlan pl = make_plan(w, nb, row_blocks, epilogue, sm_count);
+  if (pl.partial_floats * 4 > scratch.partial_bytes || pl.counters > scratch.num_counters) {
+    set_error("split-K scratch too small (%zu > %zu bytes, %zu > %zu counters): call "
+              "fb2_pregrow_scratch outside graph capture",
+              pl.partial_floats * 4, scratch.partial_bytes, pl.counters, scratch.num_counters);
+    return FB2_ERR_ARG;
+  }
+  TcParams p{};
+  p.w = w;
+  p.rm = rows;
+  p.x = x;
+  p.y = y;
+  p.partials = scratch.partials;
+  p.counters = scratch.counters;
+  p.n_tiles = pl.n_tiles;
+  p.splits = pl.splits;
+  p.gps = pl.gps;
+  p.groups = w.k / kGroup;
+  p.tiles_per_expert = w.ld / kTileN;
+  p.ld_out = epilogue ? w.n / 2 : w.n;
+  dim3 grid((unsigned)(pl.n_tiles * pl.splits), (unsigned)row_blocks);
+
+#define FB2_TC_LAUNCH(NBV, SILU)                                                    \
+  do {                                                                              \
+    int rc = set_smem(tc_decode_kernel<NBV, SILU>, pl.smem);                        \
+    if (rc) return rc;                                                              \
+    tc_decode_kernel<NBV, SILU><<<grid, kThreads, pl.smem, stream>>>(p);            \
+  } while (0)
+  if (rows.mode == ROWS_DISPATCH) {
+    set_error("internal: dispatch rows must go through launch_tc_gemm_dispatch");
+    return FB2_ERR_ARG;
+  }
+  if (epilogue) {
+    if (nb == 16) FB2_TC_LAUNCH(16, true);
+    else if (nb == 32) FB2_TC_LAUNCH(32, true);
+    else FB2_TC_LAUNCH(64, true);
+  } else {
+    if (nb == 16) FB2_TC_LAUNCH(16, false);
+    else if (nb == 32) FB2_TC_LAUNCH(32, false);
+    else FB2_TC_LAUNCH(64, false);
+  }
+#undef FB2_TC_LAUNCH
+  FB2_LAUNCH_CHECK();
+  return FB2_OK;
+}
+
+int launch_tc_gemm_dispatch(const WeightRef &w, const RowMap &rows, const DispatchTable &tbl,
+                            const __half *x, __half *y, const TcScratch &scratch, int sm_count,
+                            cudaStream_t stream) {
+  if (!tc_supported(w)) {
+    set_error("tensor-core path needs the tiled weight format");
+    return FB2_ERR_UNSUPPORTED;
+  }
+  int nb, row_blocks;
+  plan_rows(rows, 0, nb, row_blocks);
+  if (row_blocks <= 0) return FB2_OK;
+  TcPlan pl = make_plan(w, nb, row_blocks, 0, sm_count);
+  if (pl.partial_floats * 4 > scratch.partial_bytes || pl.counters > scratch.num_counters) {
+    set_error("split-K scratch too small: call fb2_pregrow_scratch outside graph capture");
+    return FB2_ERR_ARG;
+  }
+  TcParams p{};
+  p.w = w;
+  p.rm = rows;
+  p.x = x;
+  p.y = y;
+  p.partials = scratch.partials;
+  p.counters = scratch.counters;
+  p.n_tiles = pl.n_tiles;
+  p.splits = pl.splits;
+  p.gps = pl.gps;
+  p.groups = w.k / kGroup;
+  p.tiles_per_expert = w.ld / kTileN;
+  p.ld_out = w.n;
+  dim3 grid((unsigned)(pl.n_tiles * pl.splits), (unsigned)row_blocks);
+#define FB2_TC_LAUNCH_D(NBV)                                                         \
+  do {                                                                               \
+    int rc = set_smem(tc_decode_dispatch_kernel<NBV>, pl.smem);                      \
+    if (rc) return rc;                                                               \
+    tc_decode_dispatch_kernel<NBV><<<grid, kThreads, pl.smem, stream>>>(p, tbl);     \
+  } while (0)
+  if (nb == 16) FB2_TC_LAUNCH_D(16);
+  else if (nb == 32) FB2_TC_LAUNCH_D(32);
+  else FB2_TC_LAUNCH_D(64);
+#undef FB2_TC_LAUNCH_D
+  FB2_LAUNCH_CHECK();
+  return FB2_OK;
+}
+
+}  // namespace fb2

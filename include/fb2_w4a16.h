@@ -1,0 +1,244 @@
+/*
+ * fb2_w4a16.h -- C ABI of libfb2_w4a16.so: a B200-native (sm_100a) GPTQ-Int4 W4A16
+ * dequant-GEMM path that sits behind ferrum-infer-rs's own operator traits.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference checkout).  Conventions follow the reference's existing FFI
+ * (crates/ferrum-kernels/src/backend/cuda/marlin.rs:293-388): raw pointers and sizes,
+ * a CUDA stream, an `int` status (0 = ok), the caller owns every buffer it passes,
+ * and no call synchronises the stream unless it says so.  `*_forward*`/`*_gemm_*` and
+ * the `fb2_moe_*` launchers never allocate and never touch the host after launch, so
+ * they can be captured into a CUDA graph (reference requirement:
+ * crates/ferrum-kernels/src/backend/capabilities.rs:205-214).
+ *
+ * Device activations are IEEE fp16 (`uint16_t` bit patterns here so that the header
+ * needs no CUDA include); routing indices are int32; combine weights are fp32.
+ * There is no CPU fallback: every entry point that computes fails with
+ * FB2_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef FB2_W4A16_H
+#define FB2_W4A16_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB2_API __attribute__((visibility("default")))
+
+typedef uint16_t fb2_half;          /* IEEE binary16 bit pattern                       */
+typedef void *fb2_stream_t;         /* cudaStream_t / CUstream; NULL = default stream  */
+typedef struct fb2_linear fb2_linear_t; /* one GPTQ linear      (ref: Box<dyn Linear<B>>)          */
+typedef struct fb2_stack fb2_stack_t;   /* E stacked experts    (ref: Arc<dyn MarlinExpertStack<B>>) */
+
+/* Status codes.  FerrumError::unsupported -> FB2_ERR_UNSUPPORTED, FerrumError::model ->
+ * FB2_ERR_MODEL (crates/ferrum-types error kinds used by load_gptq). */
+enum {
+  FB2_OK = 0,
+  FB2_ERR_SHAPE = -1,       /* a size/stride argument violates the documented contract */
+  FB2_ERR_UNSUPPORTED = -2, /* valid GPTQ, but outside what this path implements        */
+  FB2_ERR_CUDA = -3,        /* CUDA runtime/driver error, or no sm_100 device           */
+  FB2_ERR_NCCL = -4,
+  FB2_ERR_ARG = -5,         /* NULL / inconsistent pointer arguments                    */
+  FB2_ERR_MODEL = -6        /* malformed tensors (g_idx out of range, length mismatch)  */
+};
+
+/* Library version string, e.g. "fb2-w4a16 0.1.0 (sm_100a)". */
+FB2_API const char *fb2_version(void);
+/* Thread-local message of the last failing call on this thread ("" if none). */
+FB2_API const char *fb2_last_error(void);
+/* Number of kernels this library has launched since load / since the last reset
+ * (bench.py's gpu_launches claim is read from here). */
+FB2_API uint64_t fb2_launch_count(void);
+FB2_API void fb2_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Dense GPTQ linear.
+ * Replaces BackendQuantMarlin::load_gptq (crates/ferrum-kernels/src/backend/
+ * capabilities.rs:136; CUDA impl crates/ferrum-kernels/src/backend/cuda/quant.rs:612)
+ * argument for argument, as called by GptqLinear::from_raw[_with_metadata]
+ * (crates/ferrum-quantization/src/gptq.rs:58,84):
+ *   qweight [K/8, N] i32   nibble i of word (pr, n) = row 8*pr+i
+ *   scales  [K/g, N] f32   (f16 on disk, widened by the loader; re-rounded to f16 here,
+ *                           as quant.rs:717 does)
+ *   qzeros  [K/g, N/8] i32 nibble n%8 of word (g, n/8) stores zero-1
+ *   g_idx   [K] i32 or NULL; non-trivial g_idx (act-order) must be balanced: every
+ *           group exactly `group_size` rows (native_safetensors.rs:1327-1372)
+ *   bias    [N] f32 or NULL
+ * Host pointers are borrowed for the duration of the call only.  Unlike the reference's
+ * Marlin path (quant.rs:676 rejects any zero code other than 7) arbitrary zero codes
+ * are accepted, matching the CPU reference (backend/cpu.rs:2283-2315).
+ * Errors: bits != 4 -> UNSUPPORTED; N % 8 or K % 8 or K % group_size != 0 -> SHAPE;
+ * g_idx value outside [0, K/g) -> MODEL; unbalanced act-order groups -> UNSUPPORTED.
+ * ---------------------------------------------------------------------------------- */
+FB2_API int fb2_gptq_linear_create(const int32_t *qweight, const float *scales,
+                                   const int32_t *qzeros, const int32_t *g_idx,
+                                   const float *bias, uint32_t bits, size_t group_size, size_t k,
+                                   size_t n, int device, fb2_linear_t **out);
+FB2_API void fb2_gptq_linear_destroy(fb2_linear_t *lin);
+/* Linear::in_features / out_features (crates/ferrum-kernels/src/linear.rs:107-108). */
+FB2_API size_t fb2_gptq_linear_in_features(const fb2_linear_t *lin);
+FB2_API size_t fb2_gptq_linear_out_features(const fb2_linear_t *lin);
+/* 1 when the layer was loaded with a non-trivial g_idx (quant.rs:685-711). */
+FB2_API int fb2_gptq_linear_is_act_order(const fb2_linear_t *lin);
+/* Name of the kernel family forward() will use for `m` rows ("tc-decode", "tc-prefill",
+ * "generic"): introspection for tests and the bench, not a dispatch knob. */
+FB2_API const char *fb2_gptq_linear_kernel_name(const fb2_linear_t *lin, size_t m);
+
+/* Linear::forward (crates/ferrum-kernels/src/linear.rs:123; CUDA impl
+ * quant_linear/cuda_marlin.rs:83-181): y[m, N] = x[m, K] . W^T (+ bias), fp16 in/out,
+ * fp32 accumulate.  x and y are device pointers, row-major, contiguous.  Work is
+ * appended to `stream`; no sync, no allocation.  m == 0 is a no-op. */
+FB2_API int fb2_gptq_linear_forward(const fb2_linear_t *lin, fb2_stream_t stream,
+                                    const fb2_half *x, fb2_half *y, size_t m);
+/* The same call for HOST buffers: copies x to the device, runs forward, copies y back
+ * and synchronises.  This is the "plugin call with host buffers" the end-to-end bench
+ * times; it uses a pinned staging area owned by the handle. */
+FB2_API int fb2_gptq_linear_forward_host(fb2_linear_t *lin, const fb2_half *x_host,
+                                         fb2_half *y_host, size_t m);
+
+/* Dequantise the stored weights back to the reference's [N, K] row-major matrix, in
+ * ORIGINAL (disk) k order, exactly as cpu_dequant_gptq / dequantize_gptq_with_g_idx
+ * produce it (backend/cpu.rs:2283; native_safetensors.rs:1391).  f32 output is
+ * bit-exact; f16 output equals f16_rn of it.  Device pointers. */
+FB2_API int fb2_gptq_linear_dequant_f32(const fb2_linear_t *lin, fb2_stream_t stream,
+                                        float *w_nk);
+FB2_API int fb2_gptq_linear_dequant_f16(const fb2_linear_t *lin, fb2_stream_t stream,
+                                        fb2_half *w_nk);
+
+/* Algorithmic bytes / flops of one forward (SURVEY.md 8d formula; used for roofline
+ * accounting only). */
+FB2_API uint64_t fb2_gemm_algorithmic_bytes(size_t k, size_t n, size_t m, size_t group_size,
+                                            int act_order);
+FB2_API uint64_t fb2_gemm_flops(size_t k, size_t n, size_t m);
+
+/* BackendQuantMarlin::pregrow_marlin_gather_scratch (capabilities.rs:212): make sure
+ * the per-device scratch (act-order permuted activations, split-K partials) can serve
+ * forwards of up to `max_m` rows on every linear/stack created so far on `device`.
+ * Must be called outside graph capture; create() already sizes it for m <= 64. */
+FB2_API int fb2_pregrow_scratch(int device, size_t max_m);
+
+/* ------------------------------------------------------------------------------------
+ * Stacked MoE experts.
+ * Replaces BackendQuantMarlin::load_gptq_stacked (capabilities.rs:180; CUDA impl
+ * quant.rs:768) and the MarlinExpertStack<B> trait
+ * (crates/ferrum-kernels/src/marlin_expert_stack.rs:31-109).
+ * qweights[e] / scales[e] / qzeros[e]: expert e's raw tensors, all [K, n_per_expert];
+ * one shared g_idx (or NULL).
+ * ---------------------------------------------------------------------------------- */
+FB2_API int fb2_gptq_stack_create(const int32_t *const *qweights, const float *const *scales,
+                                  const int32_t *const *qzeros, const int32_t *g_idx,
+                                  uint32_t bits, size_t group_size, size_t k,
+                                  size_t n_per_expert, size_t num_experts, int device,
+                                  fb2_stack_t **out);
+FB2_API void fb2_gptq_stack_destroy(fb2_stack_t *st);
+FB2_API size_t fb2_gptq_stack_n_per_expert(const fb2_stack_t *st);
+FB2_API size_t fb2_gptq_stack_k(const fb2_stack_t *st);
+FB2_API size_t fb2_gptq_stack_num_experts(const fb2_stack_t *st);
+/* MarlinExpertStack::zero_workspace (marlin_expert_stack.rs:57): this design has no
+ * lock workspace; kept as a no-op for trait parity. */
+FB2_API int fb2_gptq_stack_zero_workspace(const fb2_stack_t *st, fb2_stream_t stream);
+/* MarlinExpertStack::make_expert_linear (marlin_expert_stack.rs:103): a Linear view of
+ * columns [expert_offset, expert_offset + expert_n) of the stacked [K, E*n_per_expert]
+ * matrix.  The view borrows the stack's device memory: destroy it before the stack.
+ * expert_offset and expert_n must be multiples of 128 and stay inside one expert. */
+FB2_API int fb2_gptq_stack_make_expert_linear(const fb2_stack_t *st, size_t expert_offset,
+                                              size_t expert_n, const float *bias,
+                                              fb2_linear_t **out);
+/* MarlinExpertStack::gemm_phase_batched (marlin_expert_stack.rs:64-70): for each
+ * dispatch (expert, in_row, out_row, m): y[out_row .. +m, :n_per_expert] =
+ * x[in_row .. +m, :K] . W_expert^T.  `dispatches` is a HOST array of nd 4-tuples of
+ * int64; it is read during the call only (uploaded through a pinned ring, no sync). */
+typedef struct {
+  int64_t expert, in_row, out_row, m;
+} fb2_dispatch_t;
+FB2_API int fb2_gptq_stack_gemm_batched(const fb2_stack_t *st, fb2_stream_t stream,
+                                        const fb2_half *x, const fb2_dispatch_t *dispatches,
+                                        size_t nd, fb2_half *y, size_t k);
+/* MarlinExpertStack::gemm_phase_vllm (marlin_expert_stack.rs:82-96), the routed grouped
+ * GEMM keyed by moe_align_block_size outputs (device int32 arrays): for every position
+ * i < num_tokens_post_padded[0] with id = sorted_token_ids[i] < prob_m*top_k:
+ *   y[id, :] = x[id / top_k, :] . W_{expert_ids[i / block]}^T.
+ * Unlike the reference kernel the output need not be pre-zeroed.  block in {8,16,32,64}. */
+FB2_API int fb2_gptq_stack_gemm_routed(const fb2_stack_t *st, fb2_stream_t stream,
+                                       const fb2_half *x, const int32_t *sorted_token_ids,
+                                       const int32_t *expert_ids,
+                                       const int32_t *num_tokens_post_padded, fb2_half *y,
+                                       size_t prob_m, size_t block, size_t top_k,
+                                       size_t sorted_capacity);
+/* Same, with the SwiGLU epilogue fused (stack must be a gate||up stack, n_per_expert =
+ * 2*I): act[id, i] = silu(g[id, i]) * g[id, I + i]; replaces gemm_phase_vllm +
+ * B::fused_silu_mul_split (crates/ferrum-models/src/moe/dispatch.rs:1999-2048). */
+FB2_API int fb2_gptq_stack_gemm_routed_silu(const fb2_stack_t *st, fb2_stream_t stream,
+                                            const fb2_half *x, const int32_t *sorted_token_ids,
+                                            const int32_t *expert_ids,
+                                            const int32_t *num_tokens_post_padded,
+                                            fb2_half *act, size_t prob_m, size_t block,
+                                            size_t top_k, size_t sorted_capacity);
+FB2_API int fb2_gptq_stack_dequant_f32(const fb2_stack_t *st, fb2_stream_t stream,
+                                       float *w_enk);
+
+/* ------------------------------------------------------------------------------------
+ * MoE routing / post-ops.  Replace BackendMoeFused
+ * (crates/ferrum-kernels/src/backend/capabilities.rs:305-723; CUDA launchers
+ * crates/ferrum-kernels/src/backend/cuda/moe.rs).  All pointers are device pointers.
+ * ---------------------------------------------------------------------------------- */
+/* route_topk_softmax (capabilities.rs:337; kernel kernels/moe_router.cu:32): softmax over
+ * E in f32, K passes of strict-> argmax (ties -> smaller index), optional renorm.  Uses
+ * expf (not __expf) so ids/weights match the host router route_into
+ * (crates/ferrum-models/src/moe/router.rs:113-195) on the same f16-rounded logits. */
+FB2_API int fb2_moe_route_topk_softmax(fb2_stream_t stream, const fb2_half *logits,
+                                       int32_t *out_ids, float *out_weights, size_t batch,
+                                       size_t num_experts, size_t top_k, int norm_topk_prob);
+/* moe_build_pairs_by_token (capabilities.rs:407; kernels/moe_build_pairs.cu:24).  The
+ * order inside an expert's run is ascending pair id (deterministic; the reference's is
+ * atomics order). */
+FB2_API int fb2_moe_build_pairs_by_token(fb2_stream_t stream, const int32_t *expert_ids,
+                                         int32_t *pairs_by_token, int32_t *packed_token_idx,
+                                         int32_t *expert_offsets, size_t batch_x_topk,
+                                         size_t num_experts, size_t top_k);
+/* moe_align_block_size / _pair_ids (capabilities.rs:427,447;
+ * kernels/moe_align_block_size.cu:46, moe_align_block_size_pair_ids.cu:13). */
+FB2_API int fb2_moe_align_block_size(fb2_stream_t stream, const int32_t *expert_ids_per_pair,
+                                     int32_t *sorted_token_ids, int32_t *block_ids,
+                                     int32_t *total_tokens_post_pad, size_t batch_x_topk,
+                                     size_t num_experts, size_t block_size,
+                                     size_t sorted_max_size, int pair_ids);
+/* moe_combine (capabilities.rs:684; kernels/moe_combine.cu:29): out[b,h] = sum_k
+ * w[b,k] * packed_down[pairs_by_token[b,k], h]; row -1 = skip; out is overwritten. */
+FB2_API int fb2_moe_combine(fb2_stream_t stream, const fb2_half *packed_down,
+                            const int32_t *pairs_by_token, const float *pair_weights,
+                            fb2_half *out, size_t batch, size_t hidden, size_t top_k);
+/* weighted_sum_batched (capabilities.rs:565; kernels/moe_combine.cu:62): slots is
+ * [batch, top_k, hidden]. */
+FB2_API int fb2_moe_weighted_sum_batched(fb2_stream_t stream, const fb2_half *slots,
+                                         const float *weights, fb2_half *out, size_t batch,
+                                         size_t top_k, size_t hidden);
+/* B::fused_silu_mul_split / fused_gelu_tanh_mul_split
+ * (crates/ferrum-kernels/src/backend/cpu.rs:1666,1682; kernels/fused_silu_mul.cu:29,66):
+ * gate_up [tokens, 2*im] (gate || up) -> out [tokens, im]; f32 math, f16 I/O. */
+FB2_API int fb2_fused_silu_mul_split(fb2_stream_t stream, const fb2_half *gate_up,
+                                     fb2_half *out, size_t tokens, size_t im);
+FB2_API int fb2_fused_gelu_tanh_mul_split(fb2_stream_t stream, const fb2_half *gate_up,
+                                          fb2_half *out, size_t tokens, size_t im);
+
+/* The whole MoE FFN of one layer, steps 1-6 of moe_forward_bucketed
+ * (crates/ferrum-models/src/moe/dispatch.rs:1558-2192) with gather, SwiGLU and combine
+ * fused around the two grouped GEMMs:
+ *   out[b, :] = sum_k w[b,k] * down_{e(b,k)}( silu_mul( gate_up_{e(b,k)}( x[b, :] ) ) )
+ * router_logits [batch, E] f16; x, out [batch, hidden] f16 (out is overwritten);
+ * workspace: fb2_moe_ffn_workspace_bytes() bytes of device memory, caller-owned. */
+FB2_API size_t fb2_moe_ffn_workspace_bytes(const fb2_stack_t *gate_up, const fb2_stack_t *down,
+                                           size_t max_batch, size_t top_k);
+FB2_API int fb2_moe_ffn_forward(const fb2_stack_t *gate_up, const fb2_stack_t *down,
+                                fb2_stream_t stream, const fb2_half *x,
+                                const fb2_half *router_logits, fb2_half *out, size_t batch,
+                                size_t top_k, int norm_topk_prob, void *workspace,
+                                size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FB2_W4A16_H */
