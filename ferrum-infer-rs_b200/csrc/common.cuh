@@ -131,10 +131,11 @@ struct TcScratch {
   size_t num_counters;
 };
 bool tc_supported(const WeightRef &w);
-// Bytes of split-K partial scratch a forward with up to max_rows rows may need.
-size_t tc_partial_bytes(const WeightRef &w, size_t max_rows);
-size_t tc_num_counters(const WeightRef &w, size_t max_rows);
-int launch_tc_gemm(const WeightRef &w, const RowMap &rows, int max_blocks, const __half *x,
+// Split-K scratch one launch with these rows needs (0 / 0 when it does not split).
+void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count,
+                     size_t *partial_bytes, size_t *counters);
+// tbl != nullptr  <=>  rows.mode == ROWS_DISPATCH
+int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, const __half *x,
                    __half *y, int epilogue, const TcScratch &scratch, int sm_count,
                    cudaStream_t stream);
 const char *tc_kernel_name(const WeightRef &w, size_t m);

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace fb2 {
 namespace ptx {
@@ -38,8 +39,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+      printf("fb2: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
+             blockIdx.y, threadIdx.x, bar, parity);
+      __trap();
+    }
   }
 }
 

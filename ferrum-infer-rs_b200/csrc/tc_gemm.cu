@@ -30,9 +30,13 @@ namespace fb2 {
 namespace {
 
 constexpr int kStages = 5;            // smem ring depth (stages of kStageBytes)
-constexpr int kASlots = 3;            // TMEM A-operand ring (slots of one 128-k group)
-constexpr int kTmemCols = 256;        // allocation: [0,64) accumulators, [64,256) A ring
-constexpr int kTmemABase = 64;
+constexpr int kTmemCols = 256;        // allocation: [0, NACC*NB) accumulators, then the A ring
+constexpr int kMaxASlots = 3;         // TMEM A-operand ring (slots of one 128-k group, 64 columns)
+__host__ __device__ constexpr int a_base(int nacc, int nb) { return nacc * nb < 64 ? 64 : nacc * nb; }
+__host__ __device__ constexpr int a_slots(int nacc, int nb) {
+  return (kTmemCols - a_base(nacc, nb)) / 64 < kMaxASlots ? (kTmemCols - a_base(nacc, nb)) / 64
+                                                           : kMaxASlots;
+}
 constexpr int kDequantWarps = 8;
 constexpr int kThreads = 64 + kDequantWarps * 32;   // 320
 constexpr int kXBytesMax = 64 * 1024;               // activation slice held in smem
@@ -70,7 +74,7 @@ __host__ __device__ inline SmemLayout smem_layout(int nb, int gps) {
 
 // barrier indices
 enum { BAR_FULL_W = 0, BAR_EMPTY_W = kStages, BAR_FULL_A = 2 * kStages,
-       BAR_EMPTY_A = 2 * kStages + 2 * kASlots, BAR_X = 2 * kStages + 4 * kASlots,
+       BAR_EMPTY_A = 2 * kStages + 2 * kMaxASlots, BAR_X = 2 * kStages + 4 * kMaxASlots,
        BAR_ACC = BAR_X + 1, BAR_COUNT = BAR_ACC + 1 };
 static_assert(BAR_COUNT <= 32, "barrier area too small");
 
@@ -125,6 +129,9 @@ __device__ __forceinline__ void tc_decode_body(const TcParams &p, const Dispatch
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NACC = kSilu ? 2 : 1;
   constexpr int HALF = NB / 2;
+  constexpr int kASlots = a_slots(NACC, NB);
+  constexpr int kTmemABase = a_base(NACC, NB);
+  static_assert(kASlots >= 2, "TMEM A ring needs at least two slots");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / p.splits, split = blockIdx.x - tile * p.splits;
   const int blk = blockIdx.y;
@@ -242,7 +249,21 @@ __device__ __forceinline__ void tc_decode_body(const TcParams &p, const Dispatch
         const int i = idx / cpr, c8 = idx - i * cpr;
         const int ar = s_arow[i];
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (ar >= 0) v = *reinterpret_cast<const uint4 *>(xk + (size_t)ar * p.w.k + c8 * 8);
+        if (ar >= 0) {
+          if (p.w.perm == nullptr) {
+            v = *reinterpret_cast<const uint4 *>(xk + (size_t)ar * p.w.k + c8 * 8);
+          } else {
+            // act-order: sorted k position -> disk column (reference: gather_columns.cu:26-27,
+            // a separate kernel there; fused into the operand load here)
+            const int4 *pp = reinterpret_cast<const int4 *>(p.w.perm + g0 * kGroup + c8 * 8);
+            const int4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+            const unsigned short *xr = reinterpret_cast<const unsigned short *>(p.x + (size_t)ar * p.w.k);
+            v.x = (uint32_t)xr[p0.x] | ((uint32_t)xr[p0.y] << 16);
+            v.y = (uint32_t)xr[p0.z] | ((uint32_t)xr[p0.w] << 16);
+            v.z = (uint32_t)xr[p1.x] | ((uint32_t)xr[p1.y] << 16);
+            v.w = (uint32_t)xr[p1.z] | ((uint32_t)xr[p1.w] << 16);
+          }
+        }
         const uint32_t off = (uint32_t)(c8 >> 3) * (NB * 128) + (uint32_t)i * 128 +
                              (uint32_t)(((c8 & 7) ^ (i & 7)) << 4);
         *reinterpret_cast<uint4 *>(smem + L.x + off) = v;
@@ -412,6 +433,19 @@ int set_smem(K kernel, uint32_t bytes) {
   return FB2_OK;
 }
 
+void plan_rows(const RowMap &rows, int &nb, int &row_blocks) {
+  if (rows.mode == ROWS_DENSE) {
+    nb = pick_nb(rows.m);
+    row_blocks = (rows.m + nb - 1) / nb;
+  } else if (rows.mode == ROWS_DISPATCH) {
+    nb = rows.block;           // host pre-split the entries into chunks of <= rows.block rows
+    row_blocks = rows.num_dispatch;
+  } else {
+    nb = pick_nb(rows.block);
+    row_blocks = rows.max_blocks;
+  }
+}
+
 }  // namespace
 
 bool tc_supported(const WeightRef &w) {
@@ -424,39 +458,19 @@ const char *tc_kernel_name(const WeightRef &w, size_t m) {
   return tc_supported(w) ? "tc-decode" : "generic";
 }
 
-static void plan_rows(const RowMap &rows, int max_blocks, int &nb, int &row_blocks) {
-  if (rows.mode == ROWS_DENSE) {
-    nb = pick_nb(rows.m);
-    row_blocks = (rows.m + nb - 1) / nb;
-  } else if (rows.mode == ROWS_DISPATCH) {
-    nb = rows.block;           // host pre-split the entries into chunks of <= rows.block rows
-    row_blocks = rows.num_dispatch;
-  } else {
-    nb = pick_nb(rows.block);
-    row_blocks = max_blocks;
-  }
+void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count,
+                     size_t *partial_bytes, size_t *counters) {
+  int nb, row_blocks;
+  plan_rows(rows, nb, row_blocks);
+  *partial_bytes = 0;
+  *counters = 0;
+  if (row_blocks <= 0) return;
+  TcPlan pl = make_plan(w, nb, row_blocks, epilogue, sm_count);
+  *partial_bytes = pl.partial_floats * sizeof(float);
+  *counters = pl.counters;
 }
 
-size_t tc_partial_bytes(const WeightRef &w, size_t max_rows) {
-  // worst case over the row-block sizes a forward with <= max_rows rows can pick
-  size_t worst = 0;
-  for (int nb : {16, 32, 64}) {
-    const int rb = (int)((max_rows + nb - 1) / nb);
-    for (int epi = 0; epi < 2; epi++) {
-      if (epi && (w.n / 2) % kTileN) continue;
-      TcPlan pl = make_plan(w, nb, rb > 0 ? rb : 1, epi, 148);
-      worst = worst > pl.partial_floats * 4 ? worst : pl.partial_floats * 4;
-    }
-  }
-  return worst;
-}
-
-size_t tc_num_counters(const WeightRef &w, size_t max_rows) {
-  const size_t rb = (max_rows + 15) / 16;
-  return (size_t)(w.n / kTileN) * (rb > 0 ? rb : 1);
-}
-
-int launch_tc_gemm(const WeightRef &w, const RowMap &rows, int max_blocks, const __half *x,
+int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, const __half *x,
                    __half *y, int epilogue, const TcScratch &scratch, int sm_count,
                    cudaStream_t stream) {
   if (!tc_supported(w)) {
@@ -464,11 +478,15 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, int max_blocks, const
     return FB2_ERR_UNSUPPORTED;
   }
   int nb, row_blocks;
-  plan_rows(rows, max_blocks, nb, row_blocks);
+  plan_rows(rows, nb, row_blocks);
   if (row_blocks <= 0) return FB2_OK;
   if (epilogue && (w.n / 2) % kTileN) {
     set_error("SiLU epilogue needs n_per_expert/2 to be a multiple of 128");
     return FB2_ERR_SHAPE;
+  }
+  if ((rows.mode == ROWS_DISPATCH) != (tbl != nullptr) || (tbl && epilogue)) {
+    set_error("internal: dispatch table / row mode mismatch");
+    return FB2_ERR_ARG;
   }
   TcPlan pl = make_plan(w, nb, row_blocks, epilogue, sm_count);
   if (pl.partial_floats * 4 > scratch.partial_bytes || pl.counters > scratch.num_counters) {
@@ -498,11 +516,17 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, int max_blocks, const
     if (rc) return rc;                                                              \
     tc_decode_kernel<NBV, SILU><<<grid, kThreads, pl.smem, stream>>>(p);            \
   } while (0)
-  if (rows.mode == ROWS_DISPATCH) {
-    set_error("internal: dispatch rows must go through launch_tc_gemm_dispatch");
-    return FB2_ERR_ARG;
-  }
-  if (epilogue) {
+#define FB2_TC_LAUNCH_D(NBV)                                                        \
+  do {                                                                              \
+    int rc = set_smem(tc_decode_dispatch_kernel<NBV>, pl.smem);                     \
+    if (rc) return rc;                                                              \
+    tc_decode_dispatch_kernel<NBV><<<grid, kThreads, pl.smem, stream>>>(p, *tbl);   \
+  } while (0)
+  if (tbl) {
+    if (nb == 16) FB2_TC_LAUNCH_D(16);
+    else if (nb == 32) FB2_TC_LAUNCH_D(32);
+    else FB2_TC_LAUNCH_D(64);
+  } else if (epilogue) {
     if (nb == 16) FB2_TC_LAUNCH(16, true);
     else if (nb == 32) FB2_TC_LAUNCH(32, true);
     else FB2_TC_LAUNCH(64, true);
@@ -512,48 +536,6 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, int max_blocks, const
     else FB2_TC_LAUNCH(64, false);
   }
 #undef FB2_TC_LAUNCH
-  FB2_LAUNCH_CHECK();
-  return FB2_OK;
-}
-
-int launch_tc_gemm_dispatch(const WeightRef &w, const RowMap &rows, const DispatchTable &tbl,
-                            const __half *x, __half *y, const TcScratch &scratch, int sm_count,
-                            cudaStream_t stream) {
-  if (!tc_supported(w)) {
-    set_error("tensor-core path needs the tiled weight format");
-    return FB2_ERR_UNSUPPORTED;
-  }
-  int nb, row_blocks;
-  plan_rows(rows, 0, nb, row_blocks);
-  if (row_blocks <= 0) return FB2_OK;
-  TcPlan pl = make_plan(w, nb, row_blocks, 0, sm_count);
-  if (pl.partial_floats * 4 > scratch.partial_bytes || pl.counters > scratch.num_counters) {
-    set_error("split-K scratch too small: call fb2_pregrow_scratch outside graph capture");
-    return FB2_ERR_ARG;
-  }
-  TcParams p{};
-  p.w = w;
-  p.rm = rows;
-  p.x = x;
-  p.y = y;
-  p.partials = scratch.partials;
-  p.counters = scratch.counters;
-  p.n_tiles = pl.n_tiles;
-  p.splits = pl.splits;
-  p.gps = pl.gps;
-  p.groups = w.k / kGroup;
-  p.tiles_per_expert = w.ld / kTileN;
-  p.ld_out = w.n;
-  dim3 grid((unsigned)(pl.n_tiles * pl.splits), (unsigned)row_blocks);
-#define FB2_TC_LAUNCH_D(NBV)                                                         \
-  do {                                                                               \
-    int rc = set_smem(tc_decode_dispatch_kernel<NBV>, pl.smem);                      \
-    if (rc) return rc;                                                               \
-    tc_decode_dispatch_kernel<NBV><<<grid, kThreads, pl.smem, stream>>>(p, tbl);     \
-  } while (0)
-  if (nb == 16) FB2_TC_LAUNCH_D(16);
-  else if (nb == 32) FB2_TC_LAUNCH_D(32);
-  else FB2_TC_LAUNCH_D(64);
 #undef FB2_TC_LAUNCH_D
   FB2_LAUNCH_CHECK();
   return FB2_OK;
