@@ -46,6 +46,8 @@ struct DeviceScratch {
   size_t num_counters = 0;
   size_t want_partial_bytes = 0;   // high-water mark requested by create()/pregrow
   size_t want_counters = 0;
+  __half *xperm = nullptr;         // act-order: activations with columns gathered into sorted-k order
+  size_t xperm_bytes = 0;
 };
 static DeviceScratch g_scratch[kMaxDevices];
 
@@ -103,6 +105,18 @@ static int grow_scratch(int device, size_t partial_bytes, size_t counters) {
     FB2_CUDA_TRY(cudaMemset(s.counters, 0, s.want_counters * sizeof(int32_t)));
     s.num_counters = s.want_counters;
   }
+  return FB2_OK;
+}
+
+static int grow_xperm(int device, size_t bytes) {
+  DeviceScratch &s = g_scratch[device];
+  std::lock_guard<std::mutex> lock(s.mu);
+  if (bytes <= s.xperm_bytes) return FB2_OK;
+  if (s.xperm) FB2_CUDA_TRY(cudaFree(s.xperm));
+  s.xperm = nullptr;
+  s.xperm_bytes = 0;
+  FB2_CUDA_TRY(cudaMalloc((void **)&s.xperm, bytes));
+  s.xperm_bytes = bytes;
   return FB2_OK;
 }
 
@@ -295,6 +309,7 @@ static int repack_into(const RawDev &r, const int32_t *d_perm, uint8_t *tiles, s
   return FB2_OK;
 }
 
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static size_t tile_bytes(size_t k, size_t n) { return (n / kTileN) * (k / kGroup) * (size_t)kStageBytes; }
 
 // Upper bound of row blocks moe_align_block_size can emit for `pairs` pairs.
@@ -347,6 +362,10 @@ static void worst_case_requirements(const WeightRef &w, size_t rows, int sms, si
 }
 
 static int reserve_scratch_for(const WeightRef &w, int device, size_t rows) {
+  if (w.perm) {
+    int rc = grow_xperm(device, rows * (size_t)w.k * sizeof(__half));
+    if (rc) return rc;
+  }
   size_t pb, nc;
   worst_case_requirements(w, rows, g_scratch[device].sm_count, &pb, &nc);
   if (pb == 0 && nc == 0) return FB2_OK;
@@ -357,13 +376,21 @@ static int reserve_scratch_for(const WeightRef &w, int device, size_t rows) {
 // shape needs more than any before it (impossible while the stream is being captured:
 // then the caller must have called fb2_pregrow_scratch, as the reference requires of
 // pregrow_marlin_gather_scratch, capabilities.rs:205-214).
-static int run_tc(const WeightRef &w, const RowMap &rm, const DispatchTable *tbl, const __half *x,
-                  __half *y, int epilogue, int device, cudaStream_t stream) {
+static int run_tc(const WeightRef &w_in, const RowMap &rm, const DispatchTable *tbl, const __half *x,
+                  size_t x_rows, __half *y, int epilogue, int device, cudaStream_t stream) {
   int sms = 0;
   TcScratch sc = current_scratch(device, &sms);
   size_t pb = 0, nc = 0;
+  WeightRef w = w_in;
   tc_requirements(w, rm, epilogue, sms, &pb, &nc);
-  if (pb > sc.partial_bytes || nc > sc.num_counters) {
+  size_t xb = w.perm ? x_rows * (size_t)w.k * sizeof(__half) : 0;
+  size_t have_xb;
+  {
+    DeviceScratch &s = g_scratch[device];
+    std::lock_guard<std::mutex> lock(s.mu);
+    have_xb = s.xperm_bytes;
+  }
+  if (pb > sc.partial_bytes || nc > sc.num_counters || xb > have_xb) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     FB2_CUDA_TRY(cudaStreamIsCapturing(stream, &cs));
     if (cs != cudaStreamCaptureStatusNone) {
@@ -373,7 +400,18 @@ static int run_tc(const WeightRef &w, const RowMap &rm, const DispatchTable *tbl
     }
     int rc = grow_scratch(device, pb, nc);
     if (rc) return rc;
+    if ((rc = grow_xperm(device, xb))) return rc;
     sc = current_scratch(device, &sms);
+  }
+  if (w.perm) {
+    // act-order: A'[m, j] = A[m, perm[j]] once per GEMM (reference: gather_columns.cu:15 via
+    // marlin_gemm_with_perm, quant.rs:434-509); every CTA then loads its slice with 16-byte
+    // vectors instead of repeating the gather per weight tile.
+    __half *xp = g_scratch[device].xperm;
+    int rc = launch_permute_cols(x, w.perm, xp, (int)x_rows, w.k, stream);
+    if (rc) return rc;
+    x = xp;
+    w.perm = nullptr;
   }
   return launch_tc_gemm(w, rm, tbl, x, y, epilogue, sc, sms, stream);
 }
@@ -544,7 +582,7 @@ int fb2_gptq_linear_forward(const fb2_linear_t *lin, fb2_stream_t stream, const 
   rm.mode = ROWS_DENSE;
   rm.m = (int)m;
   cudaStream_t st = (cudaStream_t)stream;
-  if (tc_supported(w)) return run_tc(w, rm, nullptr, (const __half *)x, (__half *)y, 0, lin->device, st);
+  if (tc_supported(w)) return run_tc(w, rm, nullptr, (const __half *)x, m, (__half *)y, 0, lin->device, st);
   return launch_generic_gemm(w, rm, (const __half *)x, (__half *)y, 0, st);
 }
 
@@ -581,6 +619,70 @@ int fb2_gptq_linear_forward_host(fb2_linear_t *lin, const fb2_half *x_host, fb2_
   FB2_CUDA_TRY(cudaMemcpyAsync(lin->h_y, lin->d_y, m * n * 2, cudaMemcpyDeviceToHost, lin->host_stream));
   FB2_CUDA_TRY(cudaStreamSynchronize(lin->host_stream));
   memcpy(y_host, lin->h_y, m * n * 2);
+  return FB2_OK;
+}
+
+// One pinned + one device arena per device for the host-buffer batch call.
+struct HostArena {
+  std::mutex mu;
+  uint8_t *h = nullptr, *d = nullptr;
+  size_t bytes = 0;
+  cudaStream_t stream = nullptr;
+};
+static HostArena g_arena[kMaxDevices];
+
+int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
+                                       const fb2_half *const *x_host, fb2_half *const *y_host,
+                                       size_t m) {
+  if (n == 0 || m == 0) return FB2_OK;
+  if (!lins || !x_host || !y_host) { set_error("NULL argument"); return FB2_ERR_ARG; }
+  const int device = lins[0] ? lins[0]->device : -1;
+  size_t in_bytes = 0, out_bytes = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (!lins[i] || !x_host[i] || !y_host[i]) { set_error("NULL entry %zu", i); return FB2_ERR_ARG; }
+    if (lins[i]->device != device) { set_error("all linears of a batch call must share a device"); return FB2_ERR_ARG; }
+    in_bytes += align256(m * lins[i]->w.k * 2);
+    out_bytes += align256(m * lins[i]->w.n * 2);
+  }
+  FB2_CUDA_TRY(cudaSetDevice(device));
+  HostArena &A = g_arena[device];
+  std::lock_guard<std::mutex> lock(A.mu);
+  const size_t need = in_bytes + out_bytes;
+  if (need > A.bytes) {
+    if (A.h) cudaFreeHost(A.h);
+    if (A.d) cudaFree(A.d);
+    A.h = A.d = nullptr;
+    A.bytes = 0;
+    FB2_CUDA_TRY(cudaMallocHost((void **)&A.h, need));
+    FB2_CUDA_TRY(cudaMalloc((void **)&A.d, need));
+    A.bytes = need;
+    for (size_t i = 0; i < n; i++) {
+      int rc = reserve_scratch_for(view_of(lins[i]), device, std::max<size_t>(m, 64));
+      if (rc) return rc;
+    }
+  }
+  if (!A.stream) FB2_CUDA_TRY(cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking));
+  size_t off = 0;
+  for (size_t i = 0; i < n; i++) {
+    memcpy(A.h + off, x_host[i], m * lins[i]->w.k * 2);
+    off += align256(m * lins[i]->w.k * 2);
+  }
+  FB2_CUDA_TRY(cudaMemcpyAsync(A.d, A.h, in_bytes, cudaMemcpyHostToDevice, A.stream));
+  size_t xo = 0, yo = in_bytes;
+  for (size_t i = 0; i < n; i++) {
+    int rc = fb2_gptq_linear_forward(lins[i], A.stream, (const fb2_half *)(A.d + xo),
+                                     (fb2_half *)(A.d + yo), m);
+    if (rc) return rc;
+    xo += align256(m * lins[i]->w.k * 2);
+    yo += align256(m * lins[i]->w.n * 2);
+  }
+  FB2_CUDA_TRY(cudaMemcpyAsync(A.h + in_bytes, A.d + in_bytes, out_bytes, cudaMemcpyDeviceToHost, A.stream));
+  FB2_CUDA_TRY(cudaStreamSynchronize(A.stream));
+  yo = in_bytes;
+  for (size_t i = 0; i < n; i++) {
+    memcpy(y_host[i], A.h + yo, m * lins[i]->w.n * 2);
+    yo += align256(m * lins[i]->w.n * 2);
+  }
   return FB2_OK;
 }
 
@@ -805,8 +907,10 @@ int fb2_gptq_stack_gemm_batched(const fb2_stack_t *st, fb2_stream_t stream, cons
   }
   FB2_CUDA_TRY(cudaSetDevice(st->device));
   int64_t max_m = 0;
+  size_t x_rows = 0;
   for (size_t i = 0; i < nd; i++) {
     const fb2_dispatch_t &d = dispatches[i];
+    if (d.in_row >= 0 && d.m > 0) x_rows = std::max<size_t>(x_rows, (size_t)(d.in_row + d.m));
     if (d.expert < 0 || d.expert >= st->w.num_experts || d.in_row < 0 || d.out_row < 0 || d.m < 0 ||
         d.m > INT32_MAX / 4 || d.in_row > INT32_MAX / 2 || d.out_row > INT32_MAX / 2) {
       set_error("gemm_phase_batched: dispatch %zu (expert %lld, in %lld, out %lld, m %lld) invalid",
@@ -834,7 +938,7 @@ int fb2_gptq_stack_gemm_batched(const fb2_stack_t *st, fb2_stream_t stream, cons
     rm.mode = ROWS_DISPATCH;
     rm.num_dispatch = (int)cnt;
     rm.block = nb;
-    int rc = tc ? run_tc(st->w, rm, &tbl, (const __half *)x, (__half *)y, 0, st->device,
+    int rc = tc ? run_tc(st->w, rm, &tbl, (const __half *)x, x_rows, (__half *)y, 0, st->device,
                          (cudaStream_t)stream)
                 : launch_generic_gemm_dispatch(st->w, rm, tbl, (const __half *)x, (__half *)y,
                                                (cudaStream_t)stream);
@@ -874,7 +978,7 @@ static int routed_gemm(const fb2_stack_t *st, fb2_stream_t stream, const fb2_hal
   rm.max_blocks = bound;
   if (bound <= 0) return FB2_OK;
   const bool tc = tc_supported(st->w) && (!epilogue || (st->w.n / 2) % kTileN == 0);
-  if (tc) return run_tc(st->w, rm, nullptr, (const __half *)x, (__half *)y, epilogue, st->device,
+  if (tc) return run_tc(st->w, rm, nullptr, (const __half *)x, prob_m, (__half *)y, epilogue, st->device,
                         (cudaStream_t)stream);
   return launch_generic_gemm(st->w, rm, (const __half *)x, (__half *)y, epilogue, (cudaStream_t)stream);
 }
@@ -900,13 +1004,13 @@ int fb2_gptq_stack_gemm_routed_silu(const fb2_stack_t *st, fb2_stream_t stream, 
 int fb2_moe_route_topk_softmax(fb2_stream_t stream, const fb2_half *logits, int32_t *out_ids,
                                float *out_weights, size_t batch, size_t num_experts, size_t top_k,
                                int norm_topk_prob) {
-  if (batch == 0) return FB2_OK;
-  if (!logits || !out_ids || !out_weights) { set_error("NULL argument"); return FB2_ERR_ARG; }
   if (top_k == 0) { set_error("top_k must be > 0"); return FB2_ERR_ARG; }                 // router.rs:124
   if (top_k > num_experts) {                                                              // router.rs:125-130
     set_error("top_k %zu exceeds num_experts %zu", top_k, num_experts);
     return FB2_ERR_ARG;
   }
+  if (batch == 0) return FB2_OK;
+  if (!logits || !out_ids || !out_weights) { set_error("NULL argument"); return FB2_ERR_ARG; }
   if (num_experts > 12000) { set_error("num_experts %zu too large for the router kernel", num_experts); return FB2_ERR_UNSUPPORTED; }
   return launch_route_topk_softmax((const __half *)logits, out_ids, out_weights, (int)batch,
                                    (int)num_experts, (int)top_k, norm_topk_prob, (cudaStream_t)stream);
@@ -975,7 +1079,6 @@ constexpr size_t kFfnBlock = 16;
 struct FfnLayout {
   size_t ids, wts, sorted, block_ids, total, act, down, bytes, cap;
 };
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 static FfnLayout ffn_layout(size_t batch, size_t top_k, size_t num_experts, size_t inter, size_t hidden) {
   FfnLayout L;
   const size_t pairs = batch * top_k;

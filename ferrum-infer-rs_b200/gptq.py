@@ -183,6 +183,38 @@ class GptqLinear(_LinearBase):
         return self._metadata
 
 
+def forward_host_batch(linears: Sequence[_LinearBase], xs: Sequence[np.ndarray], m: int,
+                       outs: Optional[Sequence[np.ndarray]] = None) -> Sequence[np.ndarray]:
+    """fb2_gptq_linear_forward_host_batch: host f16 arrays in, host f16 arrays out, one sync."""
+    n = len(linears)
+    xs = [np.ascontiguousarray(x, dtype=np.float16) for x in xs]
+    if outs is None:
+        outs = [np.empty((m, lin.out_features()), dtype=np.float16) for lin in linears]
+    hs = (C.c_void_p * n)(*[lin._h for lin in linears])
+    xp = (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+    yp = (C.c_void_p * n)(*[y.ctypes.data for y in outs])
+    check(lib().fb2_gptq_linear_forward_host_batch(hs, n, xp, yp, m))
+    return outs
+
+
+class HostBatch:
+    """Pre-bound argument arrays for repeated forward_host_batch calls (keeps ctypes marshalling
+    out of the timed region)."""
+
+    def __init__(self, linears: Sequence[_LinearBase], xs: Sequence[np.ndarray], outs: Sequence[np.ndarray], m: int):
+        n = len(linears)
+        self._keep = (list(linears), list(xs), list(outs))
+        self.n, self.m = n, m
+        self.hs = (C.c_void_p * n)(*[lin._h for lin in linears])
+        self.xp = (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+        self.yp = (C.c_void_p * n)(*[y.ctypes.data for y in outs])
+        self.h2d_bytes = sum(int(x.nbytes) for x in xs)
+        self.d2h_bytes = sum(int(y.nbytes) for y in outs)
+
+    def run(self) -> None:
+        check(lib().fb2_gptq_linear_forward_host_batch(self.hs, self.n, self.xp, self.yp, self.m))
+
+
 # -------------------------------------------------------------------------------- stack
 class GptqExpertStack:
     """MarlinExpertStack<B> (marlin_expert_stack.rs:31-109) built by load_gptq_stacked

@@ -99,6 +99,15 @@ FB2_API int fb2_gptq_linear_forward(const fb2_linear_t *lin, fb2_stream_t stream
 FB2_API int fb2_gptq_linear_forward_host(fb2_linear_t *lin, const fb2_half *x_host,
                                          fb2_half *y_host, size_t m);
 
+/* Host-buffer batch form of the same call: y_host[i] = lins[i].forward(x_host[i], m) for
+ * i < n (all on one device).  Inputs are staged through one pinned arena, copied to the
+ * device with one transfer, the n GEMMs are enqueued back to back, outputs return with one
+ * transfer, then the call synchronises.  This is what a host-side caller that owns host
+ * tensors (the reference's CPU-backend tests, gptq_parity_test.rs:109-145) would call. */
+FB2_API int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
+                                               const fb2_half *const *x_host,
+                                               fb2_half *const *y_host, size_t m);
+
 /* Dequantise the stored weights back to the reference's [N, K] row-major matrix, in
  * ORIGINAL (disk) k order, exactly as cpu_dequant_gptq / dequantize_gptq_with_g_idx
  * produce it (backend/cpu.rs:2283; native_safetensors.rs:1391).  f32 output is
