@@ -9,6 +9,7 @@
 //   MarlinExpertStack    crates/ferrum-kernels/src/marlin_expert_stack.rs:31-109
 //   moe_forward_bucketed crates/ferrum-models/src/moe/dispatch.rs:1558-2192
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -29,6 +30,14 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(t_error, sizeof(t_error), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("FB2_DEBUG_NO_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
 }
 
 // ---------------------------------------------------------------------- device scratch

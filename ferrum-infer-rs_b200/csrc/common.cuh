@@ -38,6 +38,10 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     fb2::count_launch();                                                                \
   } while (0)
 
+// Programmatic dependent launch is on by default; FB2_DEBUG_NO_PDL=1 turns it off (a
+// measurement aid, read once -- it changes launch attributes only, never the kernels chosen).
+bool pdl_enabled();
+
 // ------------------------------------------------------------------ tiled weight format
 // The "tile stripe" layout the tensor-core kernels stream (data layout):
 //   for each 128-column tile t, for each 128-row group g (rows in act-order-SORTED k):

@@ -214,6 +214,10 @@ __global__ void dequant_tiled_kernel(const WeightRef w, int expert, OutT *__rest
 
 __global__ void permute_cols_kernel(const __half *__restrict__ x, const int32_t *__restrict__ perm,
                                     __half *__restrict__ xp, int m, int k) {
+  // PDL: let the GEMM that follows start streaming its weights now; wait for the previous GEMM
+  // (which may still be reading the shared xp scratch) before writing.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= k) return;
   const int src = perm[j];
@@ -285,9 +289,17 @@ int launch_dequant(const WeightRef &w, int expert, float *out_f32, __half *out_f
 int launch_permute_cols(const __half *x, const int32_t *perm, __half *xp, int m, int k,
                         cudaStream_t stream) {
   if (m <= 0) return FB2_OK;
-  dim3 grid((k + 255) / 256, m < 64 ? m : 64);
-  permute_cols_kernel<<<grid, 256, 0, stream>>>(x, perm, xp, m, k);
-  FB2_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((k + 255) / 256, m < 64 ? m : 64);
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, permute_cols_kernel, x, perm, xp, m, k));
+  count_launch();
   return FB2_OK;
 }
 

@@ -75,6 +75,22 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void *src
       ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
+// 16-byte cp.async (LDGSTS) global -> shared, and its mbarrier completion hook.
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+// The mbarrier gets one arrival when all cp.async issued so far by this thread have landed
+// (.noinc: the arrival is part of the barrier's initial count).
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Programmatic dependent launch (PDL).
+__device__ __forceinline__ void grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 // Make generic-proxy shared-memory writes visible to the async proxy (UMMA / TMA reads).
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -1,26 +1,44 @@
-// tc_gemm.cu -- the sm_100a tensor-core W4A16 kernels (tcgen05 / TMEM / bulk-TMA).
+// tc_gemm.cu -- the sm_100a tensor-core W4A16 kernel (tcgen05 / TMEM / bulk-TMA), persistent
+// and stream-K scheduled.
 //
 // Formulation ("swapped operands"): y^T[n, m] = sum_k W[n, k] * x[m, k].  The 128 weight
 // columns of a tile sit on the UMMA M side, the activation rows on the UMMA N side
-// (N = 16 / 32 / 64), so a decode batch of 1..64 rows needs no padding to a 128-row MMA
-// tile, and the GPTQ packing (8 consecutive k of ONE column per 32-bit word) is already
-// the K-major order the A operand wants.
+// (N = NB = 16 / 32 / 64), so a decode batch needs no padding to a 128-row MMA tile, and the
+// GPTQ packing (8 consecutive k of ONE column per 32-bit word) is already the K-major order
+// the A operand wants.
 //
-// Per CTA (one weight tile x one k-range x one row block):
-//   warp 8      bulk-TMA producer: streams 8704-byte stages (one 128x128 int4 group tile +
-//               its 128 scale/zero pairs, contiguous in HBM) into a 5-deep smem ring,
-//               completion on mbarriers (cp.async.bulk, L2 evict-first).
+// Work decomposition.  A UNIT is one 128(n) x 128(k) weight stage (8704 contiguous bytes:
+// packed int4 + the 128 scale/zero pairs of that group) applied to one block of <= NB
+// activation rows.  Units are ordered (row block, tile, [gate|up], group); the grid is one
+// persistent wave of CTAs (two per SM) and CTA c owns the contiguous unit range
+// [c*T/G, (c+1)*T/G) -- every SM streams the same number of bytes whatever N, K and the
+// split are (no wave quantisation, no host-chosen split-K factor).  A CTA range that covers
+// a whole output tile writes the output directly; ranges that cover part of a tile write an
+// fp32 partial, and the LAST contributor to arrive on that tile (self-resetting counter)
+// sums the partials in contributor order -- deterministic, and there is no lock workspace
+// for the caller to zero (reference: marlin.rs:540-546 has to).
+//
+// Per CTA:
+//   warp 8      producer: per unit one cp.async.bulk (TMA engine, L2 evict-first) for the
+//               weight stage, plus 16-byte cp.async row gathers of the activation slice
+//               [rows x 128 k] straight into the 128B-swizzled UMMA B layout; both complete on
+//               the stage's mbarrier.  The MoE row gather (x[id / top_k]) is this load.
 //   warps 0-7   dequant: LDS.128 packed words -> lop3 magic-number int4->fp16, exact
-//               (q - zero) then one fp16 multiply by the scale [ == f16_rn of the CPU
-//               reference's f32 weight ] -> tcgen05.st into a 3-slot TMEM ring as the UMMA
-//               A operand.  Weights never go back to shared memory.
+//               (q - zero), one fp16 multiply by the scale [ == f16_rn of the CPU reference's
+//               f32 weight ] -> tcgen05.st into a TMEM ring as the UMMA A operand.  Weights
+//               never go back to shared memory.
 //   warp 9      one elected thread issues tcgen05.mma (kind::f16, M=128, N=NB, K=16, A from
-//               TMEM, B = activations from shared memory, 128B-swizzled K-major),
-//               accumulating in TMEM; tcgen05.commit releases TMEM slots.
-//   warps 0-7   epilogue: tcgen05.ld the fp32 accumulator, then either store fp16 (+bias,
-//               or SiLU(gate)*up for gate||up expert tiles) or, with split-K, write an fp32
-//               partial; the LAST CTA to arrive on a tile (self-resetting counter) reduces
-//               the partials in split order -- deterministic, no lock workspace to zero.
+//               TMEM, B from the stage); tcgen05.commit frees TMEM slots and smem stages.
+//   warps 0-7   epilogue at the end of each tile segment: tcgen05.ld the fp32 accumulator,
+//               then fp16 store (+bias, or SiLU(gate)*up) or partial + last-arriver reduce.
+// The two single-thread roles sit in the two highest warps: the issue arbiter favours the
+// highest warp id of a scheduler partition.
+//
+// Programmatic dependent launch: the kernel prefetches its first weight stages (which depend
+// on no earlier kernel) before griddepcontrol.wait, so in a chain of GEMMs the weight stream
+// of GEMM i+1 starts while GEMM i drains.
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "rowmap.cuh"
@@ -29,58 +47,45 @@ namespace fb2 {
 
 namespace {
 
-constexpr int kStages = 5;            // smem ring depth (stages of kStageBytes)
-constexpr int kTmemCols = 256;        // allocation: [0, NACC*NB) accumulators, then the A ring
-constexpr int kMaxASlots = 3;         // TMEM A-operand ring (slots of one 128-k group, 64 columns)
-__host__ __device__ constexpr int a_base(int nacc, int nb) { return nacc * nb < 64 ? 64 : nacc * nb; }
-__host__ __device__ constexpr int a_slots(int nacc, int nb) {
-  return (kTmemCols - a_base(nacc, nb)) / 64 < kMaxASlots ? (kTmemCols - a_base(nacc, nb)) / 64
-                                                           : kMaxASlots;
-}
 constexpr int kDequantWarps = 8;
-constexpr int kThreads = 64 + kDequantWarps * 32;   // 320
-// Warp roles.  The issue arbiter favours the highest warp id of a scheduler partition, so the
-// two single-thread roles that everything else waits on sit in the two highest warps.
 constexpr int kWarpTma = kDequantWarps;             // 8
 constexpr int kWarpMma = kDequantWarps + 1;         // 9
-constexpr int kXBytesMax = 64 * 1024;               // activation slice held in smem
+constexpr int kThreads = (kDequantWarps + 2) * 32;  // 320
+constexpr int kTmemCols = 256;                      // [0,128) accumulators, [128,256) A ring
+constexpr int kTmemABase = 128;
+constexpr int kASlots = 2;                          // A ring: slots of one 128-k group (64 columns)
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 108 * 1024;             // per CTA (two CTAs per SM)
+
+template <int NB>
+struct StageCfg {
+  static constexpr int kXBytes = NB * 256;                                    // [2 atoms][NB][128 B]
+  static constexpr int kStride = (kXBytes + kStageBytes + 1023) & ~1023;      // x first (1024-aligned)
+  static constexpr int kStagesRaw = (kSmemBudget - 1024) / kStride;
+  static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStride + 1024;                 // + barriers / misc
+};
 
 struct TcParams {
   WeightRef w;
   RowMap rm;
   const __half *x;
   __half *y;
-  float *partials;
-  int32_t *counters;
+  float *partials;        // [grid][2][NACC * NB * 128]
+  int32_t *counters;      // [row blocks * n_tiles], zero between launches
   int n_tiles;            // output tiles per row block (N/128, or I/128 with the SiLU epilogue)
-  int splits;             // split-K factor
-  int gps;                // 128-k groups per split
   int groups;             // K / 128
   int tiles_per_expert;   // ld / 128
   int ld_out;             // output row stride
 };
 
+// barrier slots (8 bytes each)
+enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_FULL_A = 2 * kMaxStages,
+       BAR_EMPTY_A = BAR_FULL_A + 2 * kASlots, BAR_ACC = BAR_EMPTY_A + 2 * kASlots,
+       BAR_ACC_EMPTY = BAR_ACC + 1, BAR_COUNT = BAR_ACC_EMPTY + 1 };
+static_assert(BAR_COUNT * 8 <= 512, "barrier area too small");
+
 __device__ __forceinline__ float silu_mul(float g, float u) { return (g / (1.0f + expf(-g))) * u; }
-
-struct SmemLayout {
-  uint32_t x, ring, bars, misc, total;
-};
-__host__ __device__ inline SmemLayout smem_layout(int nb, int gps) {
-  SmemLayout L;
-  L.x = 0;
-  uint32_t xbytes = (uint32_t)gps * 2u * (uint32_t)nb * 128u;
-  L.ring = (xbytes + 1023u) & ~1023u;
-  L.bars = L.ring + kStages * kStageBytes;          // 8-byte aligned (8704 % 8 == 0)
-  L.misc = L.bars + 32 * 8;
-  L.total = L.misc + 16 + 2 * 64 * 4 + 16;
-  return L;
-}
-
-// barrier indices
-enum { BAR_FULL_W = 0, BAR_EMPTY_W = kStages, BAR_FULL_A = 2 * kStages,
-       BAR_EMPTY_A = 2 * kStages + 2 * kMaxASlots, BAR_X = 2 * kStages + 4 * kMaxASlots,
-       BAR_ACC = BAR_X + 1, BAR_COUNT = BAR_ACC + 1 };
-static_assert(BAR_COUNT <= 32, "barrier area too small");
 
 // Dequantise one packed word (nibble p holds k offset {0,2,4,6,1,3,5,7}[p]) into 4 half2
 // registers (k0,k1) (k2,k3) (k4,k5) (k6,k7).
@@ -128,158 +133,242 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, float *v) {
   }
 }
 
+// ---- stream-K bookkeeping (identical in every role) -------------------------------------
+__device__ __forceinline__ long long range_start(long long c, long long T, int G) { return c * T / G; }
+__device__ __forceinline__ int cta_of_unit(long long u, long long T, int G) {
+  long long c = u * G / T;
+  while (c + 1 < G && range_start(c + 1, T, G) <= u) c++;
+  while (c > 0 && range_start(c, T, G) > u) c--;
+  return (int)c;
+}
+
+// Walks the units of one CTA with 32-bit incremental state (divisions only in init()).
+struct UnitWalk {
+  int blk, tile, phase, g, r;   // position: row block, output tile, gate/up phase, k group, unit in tile
+  int left;                     // units still to process, this one included
+  int seg_r0;                   // r at which the current segment started
+  int seg_at_start;             // the current segment starts at the CTA's range start
+  __device__ __forceinline__ void init(long long u0, long long u1, int upt, int groups, int n_tiles) {
+    const long long tau = u0 / upt;
+    r = (int)(u0 - tau * upt);
+    blk = (int)(tau / n_tiles);
+    tile = (int)(tau - (long long)blk * n_tiles);
+    phase = r / groups;
+    g = r - phase * groups;
+    left = (int)(u1 - u0);
+    seg_r0 = r;
+    seg_at_start = 1;
+  }
+  __device__ __forceinline__ bool done() const { return left <= 0; }
+  __device__ __forceinline__ bool seg_last(int upt) const { return r == upt - 1 || left == 1; }
+  __device__ __forceinline__ void next(int upt, int groups, int n_tiles) {
+    const bool last = seg_last(upt);
+    left--;
+    r++;
+    if (++g == groups) { g = 0; phase++; }
+    if (r == upt) {
+      r = 0;
+      phase = 0;
+      if (++tile == n_tiles) { tile = 0; blk++; }
+    }
+    if (last) { seg_r0 = r; seg_at_start = 0; }
+  }
+};
+
+// ring position: stage index + phase parity, advanced without division
+struct RingPos {
+  int st;
+  uint32_t par;
+  __device__ __forceinline__ void advance(int stages) {
+    if (++st == stages) { st = 0; par ^= 1u; }
+  }
+};
+
 template <int NB, bool kSilu>
-__device__ __forceinline__ void tc_decode_body(const TcParams &p, const DispatchTable *tbl) {
+__device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *tbl) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  using SC = StageCfg<NB>;
   constexpr int NACC = kSilu ? 2 : 1;
   constexpr int HALF = NB / 2;
-  constexpr int kASlots = a_slots(NACC, NB);
-  constexpr int kTmemABase = a_base(NACC, NB);
-  static_assert(kASlots >= 2, "TMEM A ring needs at least two slots");
+  constexpr int S = SC::kStages;
+  static_assert(S >= 3, "smem ring too shallow");
+  static_assert(NACC * NB <= kTmemABase, "accumulators overlap the A ring");
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x / p.splits, split = blockIdx.x - tile * p.splits;
-  const int blk = blockIdx.y;
-  if (blk >= rowmap_num_blocks(p.rm, NB)) return;     // CTA-uniform, before any barrier
+  const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int upt = NACC * p.groups;                               // units per output tile
+  // Routed mode reads the padded length the align kernel (an earlier kernel) produced.
+  if (p.rm.mode == ROWS_ROUTED) ptx::grid_dependency_wait();
+  const long long T = (long long)rowmap_num_blocks(p.rm, NB) * p.n_tiles * upt;
+  const long long u0 = range_start(cta, T, G), u1 = range_start(cta + 1, T, G);
+  if (u0 >= u1) return;                                          // CTA-uniform, before any barrier
 
-  const int g0 = split * p.gps;
-  const int ng = min(p.groups, g0 + p.gps) - g0;
-  const int total_it = NACC * ng;
-  const int expert = rowmap_block_expert(p.rm, tbl, blk);
-
-  const SmemLayout L = smem_layout(NB, p.gps);
   const uint32_t smem_base = ptx::smem_u32(smem);
-  const uint32_t bars = smem_base + L.bars;
+  const uint32_t bars = smem_base + S * SC::kStride;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + L.misc);
-  int *s_flag = reinterpret_cast<int *>(smem + L.misc + 4);
-  int *s_arow = reinterpret_cast<int *>(smem + L.misc + 16);
-  int *s_crow = s_arow + 64;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + S * SC::kStride + 512);
+  int *s_flag = reinterpret_cast<int *>(smem + S * SC::kStride + 516);
 
   // ------------------------------------------------------------------ one-time setup
   if (warp == kWarpMma) {
     if (lane == 0) {
-      for (int i = 0; i < kStages; i++) {
-        ptx::mbar_init(bar(BAR_FULL_W + i), 1);
-        ptx::mbar_init(bar(BAR_EMPTY_W + i), kDequantWarps);
+      for (int i = 0; i < S; i++) {
+        ptx::mbar_init(bar(BAR_FULL + i), 1 + 32);                // expect_tx arrive + 32 cp.async arrives
+        ptx::mbar_init(bar(BAR_EMPTY + i), kDequantWarps + 1);    // 8 warps + the MMA commit
       }
       for (int i = 0; i < 2 * kASlots; i++) {
         ptx::mbar_init(bar(BAR_FULL_A + i), 4);
         ptx::mbar_init(bar(BAR_EMPTY_A + i), 1);
       }
-      ptx::mbar_init(bar(BAR_X), kDequantWarps);
       ptx::mbar_init(bar(BAR_ACC), 1);
+      ptx::mbar_init(bar(BAR_ACC_EMPTY), kDequantWarps);
       ptx::mbar_fence_init();
     }
     __syncwarp();
     ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(s_tmem));
-  } else if (warp < kDequantWarps) {
-    const int t2 = threadIdx.x;
-    if (t2 < NB) {
-      int ar = 0, cr = 0;
-      bool ok = rowmap_resolve(p.rm, tbl, NB, blk, t2, ar, cr);
-      s_arow[t2] = ok ? ar : -1;
-      s_crow[t2] = ok ? cr : -1;
-    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-
-  // first weight tile of this CTA's output tile; with the SiLU epilogue the "up" tile sits
-  // n_tiles tiles further (gate || up along N)
   const size_t tile_stride = (size_t)p.groups * kStageBytes;
-  const uint8_t *wtile0 =
-      p.w.tiles + ((size_t)expert * p.tiles_per_expert + p.w.col0 / kTileN + tile) * tile_stride +
-      (size_t)g0 * kStageBytes;
 
   if (warp == kWarpTma) {
-    // =============================================================== bulk-TMA producer
-    if (lane == 0) {
-      const uint64_t pol = ptx::policy_evict_first();
-      for (int it = 0; it < total_it; it++) {
-        const int acc = it / ng, gi = it - acc * ng;
-        const int st = it % kStages;
-        ptx::mbar_wait(bar(BAR_EMPTY_W + st), ((it / kStages) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(bar(BAR_FULL_W + st), kStageBytes);
-        const uint8_t *src = wtile0 + (size_t)acc * p.n_tiles * tile_stride + (size_t)gi * kStageBytes;
-        ptx::bulk_g2s_hint(smem_base + L.ring + st * kStageBytes, src, kStageBytes,
-                           bar(BAR_FULL_W + st), pol);
+    // ================================================================== producer
+    const uint64_t pol = ptx::policy_evict_first();
+    UnitWalk wk;
+    wk.init(u0, u1, upt, p.groups, p.n_tiles);
+    auto weight_src = [&](const UnitWalk &w_) {
+      const int expert = rowmap_block_expert(p.rm, tbl, w_.blk);
+      return p.w.tiles +
+             ((size_t)expert * p.tiles_per_expert + p.w.col0 / kTileN + w_.tile + (size_t)w_.phase * p.n_tiles) *
+                 tile_stride + (size_t)w_.g * kStageBytes;
+    };
+    // PDL prologue: weight stages depend on no earlier kernel's output -> issue up to S of them
+    // before waiting for the grid dependency.  (Routed mode already waited above: its expert
+    // ids come from the align kernel.)
+    const int n_units = wk.left;
+    const int pre = n_units < S ? n_units : S;
+    {
+      UnitWalk pw = wk;
+      for (int i = 0; i < pre; i++) {
+        const uint8_t *src = weight_src(pw);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(bar(BAR_FULL + i), kStageBytes);
+          ptx::bulk_g2s_hint(smem_base + i * SC::kStride + SC::kXBytes, src, kStageBytes, bar(BAR_FULL + i), pol);
+        }
+        __syncwarp();
+        pw.next(upt, p.groups, p.n_tiles);
       }
+    }
+    ptx::grid_dependency_wait();
+    // rows of the current block: lane i holds row i (and i + 32 for NB == 64)
+    int cur_blk = -1, nchunks = 0, arow0 = -1, arow1 = -1;
+    const uint8_t *wsrc = nullptr;
+    RingPos rp{0, 0};
+    for (int it = 0; !wk.done(); wk.next(upt, p.groups, p.n_tiles), it++, rp.advance(S)) {
+      if (wk.blk != cur_blk) {
+        cur_blk = wk.blk;
+        int ar, cr;
+        arow0 = (lane < NB && rowmap_resolve(p.rm, tbl, NB, wk.blk, lane, ar, cr)) ? ar : -1;
+        // valid rows form a prefix of the block (moe_align_block_size puts real ids first)
+        int nvalid = __popc(__ballot_sync(0xffffffffu, arow0 >= 0));
+        if (NB > 32) {
+          arow1 = rowmap_resolve(p.rm, tbl, NB, wk.blk, lane + 32, ar, cr) ? ar : -1;
+          nvalid += __popc(__ballot_sync(0xffffffffu, arow1 >= 0));
+        }
+        nchunks = nvalid * 16;
+      }
+      if (wk.g == 0 || wsrc == nullptr) wsrc = weight_src(wk);
+      const uint32_t stage_addr = smem_base + rp.st * SC::kStride;
+      if (it >= pre) {
+        ptx::mbar_wait(bar(BAR_EMPTY + rp.st), rp.par ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(bar(BAR_FULL + rp.st), kStageBytes);
+          ptx::bulk_g2s_hint(stage_addr + SC::kXBytes, wsrc, kStageBytes, bar(BAR_FULL + rp.st), pol);
+        }
+        __syncwarp();
+      }
+      wsrc += kStageBytes;
+      // activation slice: rows [0, nvalid) x 128 k, 16 chunks of 16 B per row
+      const __half *xg = p.x + (size_t)wk.g * kGroup;
+      for (int ch0 = 0; ch0 < nchunks; ch0 += 32) {             // warp-uniform trip count
+        const int ch = ch0 + lane;
+        const int i = ch >> 4, c8 = ch & 15;
+        const int ar = __shfl_sync(0xffffffffu, (NB > 32 && i >= 32) ? arow1 : arow0, i & 31);
+        if (ch < nchunks) {
+          const uint32_t dst = stage_addr + (uint32_t)(c8 >> 3) * (NB * 128) + (uint32_t)i * 128 +
+                               (uint32_t)(((c8 & 7) ^ (i & 7)) << 4);
+          ptx::cp_async_16(dst, xg + (size_t)ar * p.w.k + c8 * 8);
+        }
+      }
+      ptx::cp_async_mbar_arrive_noinc(bar(BAR_FULL + rp.st));
     }
     __syncwarp();
   } else if (warp == kWarpMma) {
     // ==================================================================== MMA issuer
-    // The branch is warp-uniform and the issue is predicated by elect.sync, so ptxas emits
-    // straight-line UTCHMMA with uniform-register operands (no per-instruction election loop).
+    // Warp-uniform branch + elect.sync predicate: ptxas emits straight-line UTCHMMA with
+    // uniform-register operands (no per-instruction election loop).
     constexpr uint32_t idesc = ptx::umma_idesc_f16(128, NB);
-    const uint64_t b_desc0 = ptx::umma_desc_kmajor_sw128(smem_base + L.x);
-    ptx::mbar_wait(bar(BAR_X), 0);
-    int slot = 0;
-    uint32_t par = 0;
-    for (int acc = 0; acc < NACC; acc++) {
-      const uint32_t d_tmem = tmem_base + acc * NB;
-      for (int gi = 0; gi < ng; gi++) {
+    UnitWalk wk;
+    wk.init(u0, u1, upt, p.groups, p.n_tiles);
+    RingPos rp{0, 0}, ap{0, 0};
+    int seg = 0;
+    uint32_t fresh = 0x3;                        // bit a: accumulator a not yet written in this segment
+    const uint64_t b_desc_ring = ptx::umma_desc_kmajor_sw128(smem_base);
+    for (; !wk.done(); wk.next(upt, p.groups, p.n_tiles), rp.advance(S), ap.advance(kASlots)) {
+      // a new segment overwrites the accumulators: the previous epilogue must have read them
+      if (fresh == 0x3 && seg > 0) ptx::mbar_wait(bar(BAR_ACC_EMPTY), (seg - 1) & 1);
+      ptx::mbar_wait(bar(BAR_FULL + rp.st), rp.par);            // activations (and weights) landed
+      ptx::fence_proxy_async_smem();                            // cp.async data -> async proxy
+      const uint64_t b_desc0 = b_desc_ring + (uint64_t)((rp.st * SC::kStride) >> 4);
+      const uint32_t d_tmem = tmem_base + wk.phase * NB;
+      const uint32_t first = (fresh >> wk.phase) & 1u;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          ptx::mbar_wait(bar(BAR_FULL_A + slot * 2 + h), par);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            // activation atom (gi, h): [NB x 64] fp16, 128 B rows; +32 B per 16-k step
-            const uint64_t b_d = b_desc0 + (uint64_t)(((gi * 2 + h) * (NB * 128)) >> 4);
-            const uint32_t a_t = tmem_base + kTmemABase + slot * 64 + h * 32;
+      for (int h = 0; h < 2; h++) {
+        ptx::mbar_wait(bar(BAR_FULL_A + ap.st * 2 + h), ap.par);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t b_d = b_desc0 + (uint64_t)((h * (NB * 128)) >> 4);
+          const uint32_t a_t = tmem_base + kTmemABase + ap.st * 64 + h * 32;
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++)
-              ptx::umma_f16_ts(d_tmem, a_t + kk * 8, b_d + (uint64_t)(kk * 2), idesc,
-                               (gi | h | kk) != 0 ? 1u : 0u);
-            ptx::tc_commit(bar(BAR_EMPTY_A + slot * 2 + h));
-          }
-          __syncwarp();
+          for (int kk = 0; kk < 4; kk++)
+            ptx::umma_f16_ts(d_tmem, a_t + kk * 8, b_d + (uint64_t)(kk * 2), idesc,
+                             (h | kk) != 0 ? 1u : (first ^ 1u));
+          ptx::tc_commit(bar(BAR_EMPTY_A + ap.st * 2 + h));
+          if (h == 1) ptx::tc_commit(bar(BAR_EMPTY + rp.st));   // stage's activation slice consumed
         }
-        if (++slot == kASlots) { slot = 0; par ^= 1; }
+        __syncwarp();
+      }
+      fresh &= ~(1u << wk.phase);
+      if (wk.seg_last(upt)) {
+        if (ptx::elect_one()) ptx::tc_commit(bar(BAR_ACC));
+        __syncwarp();
+        fresh = 0x3;
+        seg++;
       }
     }
-    if (ptx::elect_one()) ptx::tc_commit(bar(BAR_ACC));
-    __syncwarp();
   } else {
-    // ============================================= activation load, dequant, epilogue
+    // ======================================================== dequant + epilogue warps
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int h = warp >> 2;              // which 64-k half of every group this warp owns
     const int nl = q * 32 + lane;         // weight column inside the tile == TMEM lane
-    const int t2 = threadIdx.x;           // 0..255
-
-    // ---- activations -> shared memory, UMMA K-major 128B-swizzled atoms of [NB x 64]
-    {
-      const int cpr = ng * 16;            // 16-byte chunks per row (8 halves each)
-      const int total = NB * cpr;
-      const __half *xk = p.x + (size_t)g0 * kGroup;
-      for (int idx = t2; idx < total; idx += kDequantWarps * 32) {
-        const int i = idx / cpr, c8 = idx - i * cpr;
-        const int ar = s_arow[i];
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (ar >= 0) {
-          v = *reinterpret_cast<const uint4 *>(xk + (size_t)ar * p.w.k + c8 * 8);
-        }
-        const uint32_t off = (uint32_t)(c8 >> 3) * (NB * 128) + (uint32_t)i * 128 +
-                             (uint32_t)(((c8 & 7) ^ (i & 7)) << 4);
-        *reinterpret_cast<uint4 *>(smem + L.x + off) = v;
-      }
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(BAR_X));
-    }
-
-    // ---- dequant loop
-    for (int it = 0; it < total_it; it++) {
-      const int st = it % kStages;
-      const int slot = it % kASlots;
-      ptx::mbar_wait(bar(BAR_FULL_W + st), (it / kStages) & 1);
-      const uint8_t *stage = smem + L.ring + st * kStageBytes;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    UnitWalk wk;
+    wk.init(u0, u1, upt, p.groups, p.n_tiles);
+    RingPos rp{0, 0}, ap{0, 0};
+    int seg = 0;
+    ptx::grid_dependency_wait();          // before the first global write / scratch access
+    for (; !wk.done(); wk.next(upt, p.groups, p.n_tiles), rp.advance(S), ap.advance(kASlots)) {
+      const int st = rp.st, slot = ap.st;
+      const uint32_t apar = ap.par;
+      ptx::mbar_wait(bar(BAR_FULL + st), rp.par);
+      const uint8_t *stage = smem + st * SC::kStride + SC::kXBytes;
       const uint32_t sz = reinterpret_cast<const uint32_t *>(stage + kStageWBytes)[nl];
       const uint4 w0 = *reinterpret_cast<const uint4 *>(stage + (size_t)(2 * h) * 2048 + nl * 16);
       const uint4 w1 = *reinterpret_cast<const uint4 *>(stage + (size_t)(2 * h + 1) * 2048 + nl * 16);
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(BAR_EMPTY_W + st));   // stage is in registers now
+      if (lane == 0) ptx::mbar_arrive(bar(BAR_EMPTY + st));     // weights are in registers now
 
       const __half s = __ushort_as_half((unsigned short)(sz & 0xFFFF));
       const __half zl = __ushort_as_half((unsigned short)(sz >> 16));   // 1024 + z
@@ -297,71 +386,102 @@ __device__ __forceinline__ void tc_decode_body(const TcParams &p, const Dispatch
       dequant_word(w1.z, zlo, zhi, s2, r1 + 8);
       dequant_word(w1.w, zlo, zhi, s2, r1 + 12);
 
-      ptx::mbar_wait(bar(BAR_EMPTY_A + slot * 2 + h), ((it / kASlots) & 1) ^ 1);
+      ptx::mbar_wait(bar(BAR_EMPTY_A + slot * 2 + h), apar ^ 1);
       ptx::tc_fence_after();
-      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kTmemABase + slot * 64 + h * 32;
+      const uint32_t ta = lane_base + kTmemABase + slot * 64 + h * 32;
       ptx::tmem_st_x16(ta, r0);
       ptx::tmem_st_x16(ta + 16, r1);
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar(BAR_FULL_A + slot * 2 + h));
-    }
 
-    // ---- epilogue: this thread owns output column nl, activation rows [h*HALF, +HALF)
-    ptx::mbar_wait(bar(BAR_ACC), 0);
-    ptx::tc_fence_after();
-    float v[NACC][HALF];
+      if (!wk.seg_last(upt)) continue;
+
+      // ------------------------------------------------ epilogue of this tile segment
+      const int r_begin = wk.seg_r0, r_end = wk.r + 1;          // [r_begin, r_end) of [0, upt)
+      const int blk = wk.blk, tile = wk.tile, tau = wk.blk * p.n_tiles + wk.tile;
+      ptx::mbar_wait(bar(BAR_ACC), seg & 1);
+      seg++;
+      ptx::tc_fence_after();
+      float v[NACC][HALF];
 #pragma unroll
-    for (int a = 0; a < NACC; a++)
-      load_acc<NB>(tmem_base + ((uint32_t)(q * 32) << 16) + a * NB + h * HALF, v[a]);
-
-    const int col = tile * kTileN + nl;
-    if (p.splits == 1) {
+      for (int a = 0; a < NACC; a++) {
+        const bool touched = r_begin < (a + 1) * p.groups && r_end > a * p.groups;   // CTA-uniform
+        if (touched) {
+          load_acc<NB>(lane_base + a * NB + h * HALF, v[a]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < HALF; j++) v[a][j] = 0.0f;
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(BAR_ACC_EMPTY));      // accumulators may be overwritten
+      const int col = tile * kTileN + nl;
       const float bias = (!kSilu && p.w.bias) ? p.w.bias[col] : 0.0f;
-#pragma unroll
-      for (int j = 0; j < HALF; j++) {
-        const int cr = s_crow[h * HALF + j];
-        if (cr < 0) continue;
-        float o = kSilu ? silu_mul(v[0][j], v[NACC - 1][j]) : v[0][j] + bias;
-        p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
-      }
-    } else {
-      // split-K: fp32 partials, last arriver reduces in split order (deterministic)
-      const size_t tile_id = (size_t)blk * p.n_tiles + tile;
-      float *part = p.partials + (tile_id * p.splits + split) * (size_t)(NACC * NB * kTileN);
-#pragma unroll
-      for (int a = 0; a < NACC; a++)
-#pragma unroll
-        for (int j = 0; j < HALF; j++)
-          part[(size_t)(a * NB + h * HALF + j) * kTileN + nl] = v[a][j];
-      __threadfence();
-      ptx::named_bar_sync(1, kDequantWarps * 32);
-      if (t2 == 0) {
-        const int old = atomicAdd(p.counters + tile_id, 1);
-        *s_flag = (old == p.splits - 1);
-        if (old == p.splits - 1) p.counters[tile_id] = 0;   // self-reset for the next launch
-      }
-      ptx::named_bar_sync(1, kDequantWarps * 32);
-      if (*s_flag) {
-        __threadfence();
-        const float *base = p.partials + tile_id * p.splits * (size_t)(NACC * NB * kTileN);
-        const float bias = (!kSilu && p.w.bias) ? p.w.bias[col] : 0.0f;
+      if (r_begin == 0 && r_end == upt) {
+        // this CTA covered the whole tile: direct store
 #pragma unroll
         for (int j = 0; j < HALF; j++) {
-          const int cr = s_crow[h * HALF + j];
-          if (cr < 0) continue;
-          float sum[NACC];
-#pragma unroll
-          for (int a = 0; a < NACC; a++) sum[a] = 0.0f;
-          for (int s = 0; s < p.splits; s++)
-#pragma unroll
-            for (int a = 0; a < NACC; a++)
-              sum[a] += __ldcg(base + (size_t)s * (NACC * NB * kTileN) +
-                               (size_t)(a * NB + h * HALF + j) * kTileN + nl);
-          float o = kSilu ? silu_mul(sum[0], sum[NACC - 1]) : sum[0] + bias;
+          int ar, cr;
+          if (!rowmap_resolve(p.rm, tbl, NB, blk, h * HALF + j, ar, cr)) continue;
+          const float o = kSilu ? silu_mul(v[0][j], v[NACC - 1][j]) : v[0][j] + bias;
           p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
         }
+      } else {
+        // partial tile: fp32 partial, last arriver reduces in contributor order
+        constexpr int kPart = NACC * NB * kTileN;
+        const int pslot = wk.seg_at_start ? 0 : 1;
+        float *part = p.partials + ((size_t)cta * 2 + pslot) * kPart;
+#pragma unroll
+        for (int a = 0; a < NACC; a++)
+#pragma unroll
+          for (int j = 0; j < HALF; j++) part[(size_t)(a * NB + h * HALF + j) * kTileN + nl] = v[a][j];
+        __threadfence();
+        ptx::named_bar_sync(1, kDequantWarps * 32);
+        const long long tile_u0 = (long long)tau * upt;
+        const int c_first = cta_of_unit(tile_u0, T, G), c_last = cta_of_unit(tile_u0 + upt - 1, T, G);
+        if (threadIdx.x == 0) {
+          const int contributors = c_last - c_first + 1;
+          const int old = atomicAdd(p.counters + tau, 1);
+          *s_flag = (old == contributors - 1);
+          if (old == contributors - 1) p.counters[tau] = 0;   // self-reset for the next launch
+        }
+        ptx::named_bar_sync(1, kDequantWarps * 32);
+        if (*s_flag) {
+          __threadfence();
+          // Contributors outermost, rows unrolled inside: HALF * NACC independent L2 loads are in
+          // flight per step (a row-outer loop would serialise one L2 round trip per addend).
+          float sum[NACC][HALF];
+#pragma unroll
+          for (int a = 0; a < NACC; a++)
+#pragma unroll
+            for (int j = 0; j < HALF; j++) sum[a][j] = 0.0f;
+          const float *src = p.partials + ((size_t)c_first * 2 + (range_start(c_first, T, G) >= tile_u0 ? 0 : 1)) * kPart +
+                             (size_t)(h * HALF) * kTileN + nl;
+          for (int c = c_first; c <= c_last; c++) {
+            float t[NACC][HALF];
+#pragma unroll
+            for (int a = 0; a < NACC; a++)
+#pragma unroll
+              for (int j = 0; j < HALF; j++) t[a][j] = __ldcg(src + (size_t)(a * NB + j) * kTileN);
+#pragma unroll
+            for (int a = 0; a < NACC; a++)
+#pragma unroll
+              for (int j = 0; j < HALF; j++) sum[a][j] += t[a][j];
+            // every contributor after the first starts inside the tile -> its slot 0
+            src = p.partials + ((size_t)(c + 1) * 2) * kPart + (size_t)(h * HALF) * kTileN + nl;
+          }
+#pragma unroll
+          for (int j = 0; j < HALF; j++) {
+            int ar, cr;
+            if (!rowmap_resolve(p.rm, tbl, NB, blk, h * HALF + j, ar, cr)) continue;
+            const float o = kSilu ? silu_mul(sum[0][j], sum[NACC - 1][j]) : sum[0][j] + bias;
+            p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
+          }
+        }
+        ptx::named_bar_sync(1, kDequantWarps * 32);              // s_flag may be rewritten next segment
       }
     }
   }
@@ -373,61 +493,25 @@ __device__ __forceinline__ void tc_decode_body(const TcParams &p, const Dispatch
 }
 
 template <int NB, bool kSilu>
-__global__ void __launch_bounds__(kThreads, 2) tc_decode_kernel(const TcParams p) {
-  tc_decode_body<NB, kSilu>(p, nullptr);
+__global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const TcParams p) {
+  ptx::launch_dependents();
+  tc_body<NB, kSilu>(p, nullptr);
 }
 template <int NB>
 __global__ void __launch_bounds__(kThreads, 2)
-tc_decode_dispatch_kernel(const TcParams p, const __grid_constant__ DispatchTable tbl) {
-  tc_decode_body<NB, false>(p, &tbl);
+tc_gemm_dispatch_kernel(const TcParams p, const __grid_constant__ DispatchTable tbl) {
+  ptx::launch_dependents();
+  tc_body<NB, false>(p, &tbl);
 }
 
 // ------------------------------------------------------------------------ host planning
 struct TcPlan {
-  int nb, row_blocks, n_tiles, splits, gps, nacc;
+  int nb, row_blocks, n_tiles, nacc, grid;
   size_t partial_floats, counters;
   uint32_t smem;
 };
 
 int pick_nb(int rows_per_block) { return rows_per_block <= 16 ? 16 : rows_per_block <= 32 ? 32 : 64; }
-
-TcPlan make_plan(const WeightRef &w, int nb, int row_blocks, int epilogue, int sm_count) {
-  TcPlan pl{};
-  pl.nb = nb;
-  pl.row_blocks = row_blocks;
-  pl.nacc = epilogue ? 2 : 1;
-  pl.n_tiles = (epilogue ? w.n / 2 : w.n) / kTileN;
-  const int groups = w.k / kGroup;
-  const int gps_cap = kXBytesMax / (nb * 256);            // activation slice must fit
-  const int s_min = (groups + gps_cap - 1) / gps_cap;
-  const long tiles = (long)pl.n_tiles * row_blocks;
-  const long slots = 2L * (sm_count > 0 ? sm_count : 148);
-  // cost model in units of one stage time: waves * (stages per CTA + fixed overhead)
-  double best = 1e30;
-  int best_s = s_min;
-  for (int s = s_min; s <= groups; s++) {
-    const int gps = (groups + s - 1) / s;
-    const int s_eff = (groups + gps - 1) / gps;
-    if (s_eff != s) continue;
-    const long ctas = tiles * s;
-    const long waves = (ctas + slots - 1) / slots;
-    const double cost = (double)waves * (gps * pl.nacc + 3.0) + (s > 1 ? 0.5 + 0.05 * s : 0.0);
-    if (cost < best - 1e-9) { best = cost; best_s = s; }
-    if (ctas >= 8 * slots) break;
-  }
-  pl.splits = best_s;
-  pl.gps = (groups + best_s - 1) / best_s;
-  pl.partial_floats = pl.splits > 1 ? (size_t)tiles * pl.splits * pl.nacc * nb * kTileN : 0;
-  pl.counters = pl.splits > 1 ? (size_t)tiles : 0;
-  pl.smem = smem_layout(nb, pl.gps).total;
-  return pl;
-}
-
-template <typename K>
-int set_smem(K kernel, uint32_t bytes) {
-  FB2_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return FB2_OK;
-}
 
 void plan_rows(const RowMap &rows, int &nb, int &row_blocks) {
   if (rows.mode == ROWS_DENSE) {
@@ -442,6 +526,54 @@ void plan_rows(const RowMap &rows, int &nb, int &row_blocks) {
   }
 }
 
+TcPlan make_plan(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count) {
+  TcPlan pl{};
+  plan_rows(rows, pl.nb, pl.row_blocks);
+  pl.nacc = epilogue ? 2 : 1;
+  pl.n_tiles = (epilogue ? w.n / 2 : w.n) / kTileN;
+  const long long units = (long long)pl.row_blocks * pl.n_tiles * pl.nacc * (w.k / kGroup);
+  const int slots = 2 * (sm_count > 0 ? sm_count : 148);
+  long long g = units / 2;                       // >= 2 units per CTA: amortise setup / epilogue
+  if (g < 1) g = 1;
+  pl.grid = (int)(g < slots ? g : slots);
+  pl.partial_floats = (size_t)pl.grid * 2 * pl.nacc * pl.nb * kTileN;
+  pl.counters = (size_t)pl.row_blocks * pl.n_tiles;
+  pl.smem = pl.nb == 16 ? StageCfg<16>::kSmemBytes : pl.nb == 32 ? StageCfg<32>::kSmemBytes : StageCfg<64>::kSmemBytes;
+  return pl;
+}
+
+int launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, const TcPlan &pl, cudaStream_t stream) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3((unsigned)pl.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return FB2_OK;
+}
+
+template <int NB, bool kSilu>
+int launch_plain(const TcPlan &pl, cudaStream_t stream, const TcParams &p) {
+  FB2_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<NB, kSilu>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  launch_cfg(cfg, attr, pl, stream);
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NB, kSilu>, p));
+  return FB2_OK;
+}
+template <int NB>
+int launch_dispatch(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const DispatchTable &tbl) {
+  FB2_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_dispatch_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  launch_cfg(cfg, attr, pl, stream);
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_dispatch_kernel<NB>, p, tbl));
+  return FB2_OK;
+}
+
 }  // namespace
 
 bool tc_supported(const WeightRef &w) {
@@ -451,17 +583,17 @@ bool tc_supported(const WeightRef &w) {
 
 const char *tc_kernel_name(const WeightRef &w, size_t m) {
   (void)m;
-  return tc_supported(w) ? "tc-decode" : "generic";
+  return tc_supported(w) ? "tc-streamk" : "generic";
 }
 
 void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count,
                      size_t *partial_bytes, size_t *counters) {
-  int nb, row_blocks;
-  plan_rows(rows, nb, row_blocks);
   *partial_bytes = 0;
   *counters = 0;
+  int nb, row_blocks;
+  plan_rows(rows, nb, row_blocks);
   if (row_blocks <= 0) return;
-  TcPlan pl = make_plan(w, nb, row_blocks, epilogue, sm_count);
+  TcPlan pl = make_plan(w, rows, epilogue, sm_count);
   *partial_bytes = pl.partial_floats * sizeof(float);
   *counters = pl.counters;
 }
@@ -484,7 +616,7 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
     set_error("internal: dispatch table / row mode mismatch");
     return FB2_ERR_ARG;
   }
-  TcPlan pl = make_plan(w, nb, row_blocks, epilogue, sm_count);
+  TcPlan pl = make_plan(w, rows, epilogue, sm_count);
   if (pl.partial_floats * 4 > scratch.partial_bytes || pl.counters > scratch.num_counters) {
     set_error("split-K scratch too small (%zu > %zu bytes, %zu > %zu counters): call "
               "fb2_pregrow_scratch outside graph capture",
@@ -499,41 +631,23 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   p.partials = scratch.partials;
   p.counters = scratch.counters;
   p.n_tiles = pl.n_tiles;
-  p.splits = pl.splits;
-  p.gps = pl.gps;
   p.groups = w.k / kGroup;
   p.tiles_per_expert = w.ld / kTileN;
   p.ld_out = epilogue ? w.n / 2 : w.n;
-  dim3 grid((unsigned)(pl.n_tiles * pl.splits), (unsigned)row_blocks);
 
-#define FB2_TC_LAUNCH(NBV, SILU)                                                    \
-  do {                                                                              \
-    int rc = set_smem(tc_decode_kernel<NBV, SILU>, pl.smem);                        \
-    if (rc) return rc;                                                              \
-    tc_decode_kernel<NBV, SILU><<<grid, kThreads, pl.smem, stream>>>(p);            \
-  } while (0)
-#define FB2_TC_LAUNCH_D(NBV)                                                        \
-  do {                                                                              \
-    int rc = set_smem(tc_decode_dispatch_kernel<NBV>, pl.smem);                     \
-    if (rc) return rc;                                                              \
-    tc_decode_dispatch_kernel<NBV><<<grid, kThreads, pl.smem, stream>>>(p, *tbl);   \
-  } while (0)
+  int rc;
   if (tbl) {
-    if (nb == 16) FB2_TC_LAUNCH_D(16);
-    else if (nb == 32) FB2_TC_LAUNCH_D(32);
-    else FB2_TC_LAUNCH_D(64);
+    rc = nb == 16 ? launch_dispatch<16>(pl, stream, p, *tbl)
+         : nb == 32 ? launch_dispatch<32>(pl, stream, p, *tbl) : launch_dispatch<64>(pl, stream, p, *tbl);
   } else if (epilogue) {
-    if (nb == 16) FB2_TC_LAUNCH(16, true);
-    else if (nb == 32) FB2_TC_LAUNCH(32, true);
-    else FB2_TC_LAUNCH(64, true);
+    rc = nb == 16 ? launch_plain<16, true>(pl, stream, p)
+         : nb == 32 ? launch_plain<32, true>(pl, stream, p) : launch_plain<64, true>(pl, stream, p);
   } else {
-    if (nb == 16) FB2_TC_LAUNCH(16, false);
-    else if (nb == 32) FB2_TC_LAUNCH(32, false);
-    else FB2_TC_LAUNCH(64, false);
+    rc = nb == 16 ? launch_plain<16, false>(pl, stream, p)
+         : nb == 32 ? launch_plain<32, false>(pl, stream, p) : launch_plain<64, false>(pl, stream, p);
   }
-#undef FB2_TC_LAUNCH
-#undef FB2_TC_LAUNCH_D
-  FB2_LAUNCH_CHECK();
+  if (rc) return rc;
+  count_launch();
   return FB2_OK;
 }
 

@@ -72,7 +72,7 @@ def test_cuda_vs_cpu(fb2, oracle, cuda):
     syn, _ = _make(oracle, 512, 256, 128, 0xC0FFEE)
     lin = fb2.GptqLinear.from_raw(syn.qweight, syn.scales, syn.qzeros, None, None, 4, 128, 512, 256)
     x = oracle.f16_round(np.cos(np.arange(2 * 512, dtype=np.float32) * np.float32(0.003))).reshape(2, 512)
-    assert lin.kernel_name(2) == "tc-decode"
+    assert lin.kernel_name(2) == "tc-streamk"
     _check_forward(oracle, cuda, lin, syn, None, 2, x=x)
 
 
