@@ -37,6 +37,8 @@
 // Programmatic dependent launch: the kernel prefetches its first weight stages (which depend
 // on no earlier kernel) before griddepcontrol.wait, so in a chain of GEMMs the weight stream
 // of GEMM i+1 starts while GEMM i drains.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -142,36 +144,34 @@ __device__ __forceinline__ int cta_of_unit(long long u, long long T, int G) {
   return (int)c;
 }
 
-// Walks the units of one CTA with 32-bit incremental state (divisions only in init()).
-struct UnitWalk {
-  int blk, tile, phase, g, r;   // position: row block, output tile, gate/up phase, k group, unit in tile
-  int left;                     // units still to process, this one included
-  int seg_r0;                   // r at which the current segment started
-  int seg_at_start;             // the current segment starts at the CTA's range start
-  __device__ __forceinline__ void init(long long u0, long long u1, int upt, int groups, int n_tiles) {
+// One CTA's unit range, cut into SEGMENTS: maximal runs of units that belong to one output
+// tile (row block, tile).  r0/r1 index the tile's unit list [gate groups..., up groups...].
+struct Seg {
+  int blk, tile, r0, r1;
+  int at_start;              // the segment starts at the CTA's range start (partial slot 0)
+};
+struct SegIter {
+  int blk, tile, r, left, first;
+  __device__ __forceinline__ void init(long long u0, long long u1, int upt, int n_tiles) {
     const long long tau = u0 / upt;
     r = (int)(u0 - tau * upt);
     blk = (int)(tau / n_tiles);
     tile = (int)(tau - (long long)blk * n_tiles);
-    phase = r / groups;
-    g = r - phase * groups;
     left = (int)(u1 - u0);
-    seg_r0 = r;
-    seg_at_start = 1;
+    first = 1;
   }
-  __device__ __forceinline__ bool done() const { return left <= 0; }
-  __device__ __forceinline__ bool seg_last(int upt) const { return r == upt - 1 || left == 1; }
-  __device__ __forceinline__ void next(int upt, int groups, int n_tiles) {
-    const bool last = seg_last(upt);
-    left--;
-    r++;
-    if (++g == groups) { g = 0; phase++; }
+  __device__ __forceinline__ bool next(Seg &s, int upt, int n_tiles) {
+    if (left <= 0) return false;
+    const int n = min(left, upt - r);
+    s.blk = blk; s.tile = tile; s.r0 = r; s.r1 = r + n; s.at_start = first;
+    first = 0;
+    left -= n;
+    r += n;
     if (r == upt) {
       r = 0;
-      phase = 0;
       if (++tile == n_tiles) { tile = 0; blk++; }
     }
-    if (last) { seg_r0 = r; seg_at_start = 0; }
+    return true;
   }
 };
 
@@ -194,12 +194,20 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   static_assert(S >= 3, "smem ring too shallow");
   static_assert(NACC * NB <= kTmemABase, "accumulators overlap the A ring");
 
+#ifdef FB2_TIMELINE
+  const long long t_entry = clock64();
+  long long tl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define FB2_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) tl[i] = clock64() - t_entry; } while (0)
+#else
+#define FB2_STAMP(i) do { } while (0)
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = (int)gridDim.x, cta = (int)blockIdx.x;
-  const int upt = NACC * p.groups;                               // units per output tile
+  const int groups = p.groups, n_tiles = p.n_tiles;
+  const int upt = NACC * groups;                                 // units per output tile
   // Routed mode reads the padded length the align kernel (an earlier kernel) produced.
   if (p.rm.mode == ROWS_ROUTED) ptx::grid_dependency_wait();
-  const long long T = (long long)rowmap_num_blocks(p.rm, NB) * p.n_tiles * upt;
+  const long long T = (long long)rowmap_num_blocks(p.rm, NB) * n_tiles * upt;
   const long long u0 = range_start(cta, T, G), u1 = range_start(cta + 1, T, G);
   if (u0 >= u1) return;                                          // CTA-uniform, before any barrier
 
@@ -208,14 +216,25 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + S * SC::kStride + 512);
   int *s_flag = reinterpret_cast<int *>(smem + S * SC::kStride + 516);
+  const size_t tile_stride = (size_t)groups * kStageBytes;
 
   // ------------------------------------------------------------------ one-time setup
-  if (warp == kWarpMma) {
+  // The producer owns the stage barriers and starts streaming weights at once; TMEM
+  // allocation and the other barriers proceed in parallel on the MMA warp.
+  if (warp == kWarpTma) {
     if (lane == 0) {
       for (int i = 0; i < S; i++) {
         ptx::mbar_init(bar(BAR_FULL + i), 1 + 32);                // expect_tx arrive + 32 cp.async arrives
         ptx::mbar_init(bar(BAR_EMPTY + i), kDequantWarps + 1);    // 8 warps + the MMA commit
       }
+      ptx::mbar_fence_init();
+    }
+    __syncwarp();
+    // "stage barriers are live": the producer does not wait for TMEM allocation, the other
+    // warps do not wait for the producer's prologue (named barrier 2: arrive vs sync)
+    ptx::named_bar_arrive(2, kThreads);
+  } else if (warp == kWarpMma) {
+    if (lane == 0) {
       for (int i = 0; i < 2 * kASlots; i++) {
         ptx::mbar_init(bar(BAR_FULL_A + i), 4);
         ptx::mbar_init(bar(BAR_EMPTY_A + i), 1);
@@ -227,82 +246,104 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     __syncwarp();
     ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(s_tmem));
   }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
-  const size_t tile_stride = (size_t)p.groups * kStageBytes;
+
+  const uint64_t pol = ptx::policy_evict_first();
+  auto weight_src = [&](int blk, int tile, int phase, int g) {
+      const int expert = rowmap_block_expert(p.rm, tbl, blk);
+      return p.w.tiles +
+             ((size_t)expert * p.tiles_per_expert + p.w.col0 / kTileN + tile + (size_t)phase * n_tiles) *
+               tile_stride + (size_t)g * kStageBytes;
+  };
+  // PDL prologue: weight stages depend on no earlier kernel's output -> up to S of them are
+  // issued before the grid dependency (and before the rest of the CTA finished its setup).
+  int pre = 0;
+  if (warp == kWarpTma) {
+    {
+      SegIter si;
+      si.init(u0, u1, upt, n_tiles);
+      Seg sg;
+      while (pre < S && si.next(sg, upt, n_tiles)) {
+#pragma unroll 1
+        for (int a = 0; a < NACC; a++) {
+          const int g0 = max(sg.r0, a * groups) - a * groups, g1 = min(sg.r1, (a + 1) * groups) - a * groups;
+          if (g0 >= g1) continue;
+          const uint8_t *src = weight_src(sg.blk, sg.tile, a, g0);
+#pragma unroll 1
+          for (int g = g0; g < g1 && pre < S; g++, pre++, src += kStageBytes) {
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(bar(BAR_FULL + pre), kStageBytes);
+              ptx::bulk_g2s_hint(smem_base + pre * SC::kStride + SC::kXBytes, src, kStageBytes, bar(BAR_FULL + pre), pol);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+
+  uint32_t tmem_base = 0;
+  if (warp != kWarpTma) {
+    ptx::tc_fence_before();
+    ptx::named_bar_sync(2, kThreads);
+    ptx::tc_fence_after();
+    tmem_base = *s_tmem;
+  }
 
   if (warp == kWarpTma) {
     // ================================================================== producer
-    const uint64_t pol = ptx::policy_evict_first();
-    UnitWalk wk;
-    wk.init(u0, u1, upt, p.groups, p.n_tiles);
-    auto weight_src = [&](const UnitWalk &w_) {
-      const int expert = rowmap_block_expert(p.rm, tbl, w_.blk);
-      return p.w.tiles +
-             ((size_t)expert * p.tiles_per_expert + p.w.col0 / kTileN + w_.tile + (size_t)w_.phase * p.n_tiles) *
-                 tile_stride + (size_t)w_.g * kStageBytes;
-    };
-    // PDL prologue: weight stages depend on no earlier kernel's output -> issue up to S of them
-    // before waiting for the grid dependency.  (Routed mode already waited above: its expert
-    // ids come from the align kernel.)
-    const int n_units = wk.left;
-    const int pre = n_units < S ? n_units : S;
-    {
-      UnitWalk pw = wk;
-      for (int i = 0; i < pre; i++) {
-        const uint8_t *src = weight_src(pw);
-        if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(bar(BAR_FULL + i), kStageBytes);
-          ptx::bulk_g2s_hint(smem_base + i * SC::kStride + SC::kXBytes, src, kStageBytes, bar(BAR_FULL + i), pol);
-        }
-        __syncwarp();
-        pw.next(upt, p.groups, p.n_tiles);
-      }
-    }
     ptx::grid_dependency_wait();
     // rows of the current block: lane i holds row i (and i + 32 for NB == 64)
     int cur_blk = -1, nchunks = 0, arow0 = -1, arow1 = -1;
-    const uint8_t *wsrc = nullptr;
     RingPos rp{0, 0};
-    for (int it = 0; !wk.done(); wk.next(upt, p.groups, p.n_tiles), it++, rp.advance(S)) {
-      if (wk.blk != cur_blk) {
-        cur_blk = wk.blk;
+    int it = 0;
+    SegIter si;
+    si.init(u0, u1, upt, n_tiles);
+    Seg sg;
+    while (si.next(sg, upt, n_tiles)) {
+      if (sg.blk != cur_blk) {
+        cur_blk = sg.blk;
         int ar, cr;
-        arow0 = (lane < NB && rowmap_resolve(p.rm, tbl, NB, wk.blk, lane, ar, cr)) ? ar : -1;
+        arow0 = (lane < NB && rowmap_resolve(p.rm, tbl, NB, sg.blk, lane, ar, cr)) ? ar : -1;
         // valid rows form a prefix of the block (moe_align_block_size puts real ids first)
         int nvalid = __popc(__ballot_sync(0xffffffffu, arow0 >= 0));
         if (NB > 32) {
-          arow1 = rowmap_resolve(p.rm, tbl, NB, wk.blk, lane + 32, ar, cr) ? ar : -1;
+          arow1 = rowmap_resolve(p.rm, tbl, NB, sg.blk, lane + 32, ar, cr) ? ar : -1;
           nvalid += __popc(__ballot_sync(0xffffffffu, arow1 >= 0));
         }
         nchunks = nvalid * 16;
       }
-      if (wk.g == 0 || wsrc == nullptr) wsrc = weight_src(wk);
-      const uint32_t stage_addr = smem_base + rp.st * SC::kStride;
-      if (it >= pre) {
-        ptx::mbar_wait(bar(BAR_EMPTY + rp.st), rp.par ^ 1u);
-        if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(bar(BAR_FULL + rp.st), kStageBytes);
-          ptx::bulk_g2s_hint(stage_addr + SC::kXBytes, wsrc, kStageBytes, bar(BAR_FULL + rp.st), pol);
+#pragma unroll 1
+      for (int a = 0; a < NACC; a++) {
+        const int g0 = max(sg.r0, a * groups) - a * groups, g1 = min(sg.r1, (a + 1) * groups) - a * groups;
+        if (g0 >= g1) continue;
+        const uint8_t *wsrc = weight_src(sg.blk, sg.tile, a, g0);
+        const __half *xg = p.x + (size_t)g0 * kGroup;
+#pragma unroll 1
+        for (int g = g0; g < g1; g++, it++, wsrc += kStageBytes, xg += kGroup, rp.advance(S)) {
+          const uint32_t stage_addr = smem_base + rp.st * SC::kStride;
+          const uint32_t full = bar(BAR_FULL + rp.st);
+          if (it >= pre) {
+            ptx::mbar_wait(bar(BAR_EMPTY + rp.st), rp.par ^ 1u);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(full, kStageBytes);
+              ptx::bulk_g2s_hint(stage_addr + SC::kXBytes, wsrc, kStageBytes, full, pol);
+            }
+            __syncwarp();
+          }
+          // activation slice: rows [0, nvalid) x 128 k, 16 chunks of 16 B per row
+          for (int ch0 = 0; ch0 < nchunks; ch0 += 32) {           // warp-uniform trip count
+            const int ch = ch0 + lane;
+            const int i = ch >> 4, c8 = ch & 15;
+            const int ar = __shfl_sync(0xffffffffu, (NB > 32 && i >= 32) ? arow1 : arow0, i & 31);
+            if (ch < nchunks) {
+              const uint32_t dst = stage_addr + (uint32_t)(c8 >> 3) * (NB * 128) + (uint32_t)i * 128 +
+                                   (uint32_t)(((c8 & 7) ^ (i & 7)) << 4);
+              ptx::cp_async_16(dst, xg + (size_t)ar * p.w.k + c8 * 8);
+            }
+          }
+          ptx::cp_async_mbar_arrive_noinc(full);
         }
-        __syncwarp();
       }
-      wsrc += kStageBytes;
-      // activation slice: rows [0, nvalid) x 128 k, 16 chunks of 16 B per row
-      const __half *xg = p.x + (size_t)wk.g * kGroup;
-      for (int ch0 = 0; ch0 < nchunks; ch0 += 32) {             // warp-uniform trip count
-        const int ch = ch0 + lane;
-        const int i = ch >> 4, c8 = ch & 15;
-        const int ar = __shfl_sync(0xffffffffu, (NB > 32 && i >= 32) ? arow1 : arow0, i & 31);
-        if (ch < nchunks) {
-          const uint32_t dst = stage_addr + (uint32_t)(c8 >> 3) * (NB * 128) + (uint32_t)i * 128 +
-                               (uint32_t)(((c8 & 7) ^ (i & 7)) << 4);
-          ptx::cp_async_16(dst, xg + (size_t)ar * p.w.k + c8 * 8);
-        }
-      }
-      ptx::cp_async_mbar_arrive_noinc(bar(BAR_FULL + rp.st));
     }
     __syncwarp();
   } else if (warp == kWarpMma) {
@@ -310,43 +351,46 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     // Warp-uniform branch + elect.sync predicate: ptxas emits straight-line UTCHMMA with
     // uniform-register operands (no per-instruction election loop).
     constexpr uint32_t idesc = ptx::umma_idesc_f16(128, NB);
-    UnitWalk wk;
-    wk.init(u0, u1, upt, p.groups, p.n_tiles);
+    const uint64_t b_desc_ring = ptx::umma_desc_kmajor_sw128(smem_base);
     RingPos rp{0, 0}, ap{0, 0};
     int seg = 0;
-    uint32_t fresh = 0x3;                        // bit a: accumulator a not yet written in this segment
-    const uint64_t b_desc_ring = ptx::umma_desc_kmajor_sw128(smem_base);
-    for (; !wk.done(); wk.next(upt, p.groups, p.n_tiles), rp.advance(S), ap.advance(kASlots)) {
-      // a new segment overwrites the accumulators: the previous epilogue must have read them
-      if (fresh == 0x3 && seg > 0) ptx::mbar_wait(bar(BAR_ACC_EMPTY), (seg - 1) & 1);
-      ptx::mbar_wait(bar(BAR_FULL + rp.st), rp.par);            // activations (and weights) landed
-      ptx::fence_proxy_async_smem();                            // cp.async data -> async proxy
-      const uint64_t b_desc0 = b_desc_ring + (uint64_t)((rp.st * SC::kStride) >> 4);
-      const uint32_t d_tmem = tmem_base + wk.phase * NB;
-      const uint32_t first = (fresh >> wk.phase) & 1u;
+    SegIter si;
+    si.init(u0, u1, upt, n_tiles);
+    Seg sg;
+    while (si.next(sg, upt, n_tiles)) {
+      // this segment overwrites the accumulators: the previous epilogue must have read them
+      if (seg > 0) ptx::mbar_wait(bar(BAR_ACC_EMPTY), (seg - 1) & 1);
+#pragma unroll 1
+      for (int a = 0; a < NACC; a++) {
+        const int g0 = max(sg.r0, a * groups), g1 = min(sg.r1, (a + 1) * groups);
+        const uint32_t d_tmem = tmem_base + a * NB;
+#pragma unroll 1
+        for (int g = g0; g < g1; g++, rp.advance(S), ap.advance(kASlots)) {
+          ptx::mbar_wait(bar(BAR_FULL + rp.st), rp.par);          // activations (and weights) landed
+          ptx::fence_proxy_async_smem();                          // cp.async data -> async proxy
+          const uint64_t b_desc0 = b_desc_ring + (uint64_t)((rp.st * SC::kStride) >> 4);
+          const uint32_t acc_flag = g != g0 ? 1u : 0u;            // first unit of a phase zero-inits
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        ptx::mbar_wait(bar(BAR_FULL_A + ap.st * 2 + h), ap.par);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint64_t b_d = b_desc0 + (uint64_t)((h * (NB * 128)) >> 4);
-          const uint32_t a_t = tmem_base + kTmemABase + ap.st * 64 + h * 32;
+          for (int h = 0; h < 2; h++) {
+            ptx::mbar_wait(bar(BAR_FULL_A + ap.st * 2 + h), ap.par);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint64_t b_d = b_desc0 + (uint64_t)((h * (NB * 128)) >> 4);
+              const uint32_t a_t = tmem_base + kTmemABase + ap.st * 64 + h * 32;
 #pragma unroll
-          for (int kk = 0; kk < 4; kk++)
-            ptx::umma_f16_ts(d_tmem, a_t + kk * 8, b_d + (uint64_t)(kk * 2), idesc,
-                             (h | kk) != 0 ? 1u : (first ^ 1u));
-          ptx::tc_commit(bar(BAR_EMPTY_A + ap.st * 2 + h));
-          if (h == 1) ptx::tc_commit(bar(BAR_EMPTY + rp.st));   // stage's activation slice consumed
+              for (int kk = 0; kk < 4; kk++)
+                ptx::umma_f16_ts(d_tmem, a_t + kk * 8, b_d + (uint64_t)(kk * 2), idesc,
+                                 (h | kk) != 0 ? 1u : acc_flag);
+              ptx::tc_commit(bar(BAR_EMPTY_A + ap.st * 2 + h));
+              if (h == 1) ptx::tc_commit(bar(BAR_EMPTY + rp.st)); // stage's activation slice consumed
+            }
+            __syncwarp();
+          }
         }
-        __syncwarp();
       }
-      fresh &= ~(1u << wk.phase);
-      if (wk.seg_last(upt)) {
-        if (ptx::elect_one()) ptx::tc_commit(bar(BAR_ACC));
-        __syncwarp();
-        fresh = 0x3;
-        seg++;
-      }
+      if (ptx::elect_one()) ptx::tc_commit(bar(BAR_ACC));
+      __syncwarp();
+      seg++;
     }
   } else {
     // ======================================================== dequant + epilogue warps
@@ -354,60 +398,68 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     const int h = warp >> 2;              // which 64-k half of every group this warp owns
     const int nl = q * 32 + lane;         // weight column inside the tile == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    UnitWalk wk;
-    wk.init(u0, u1, upt, p.groups, p.n_tiles);
+    const uint32_t w_off = SC::kXBytes + (uint32_t)h * 4096u + (uint32_t)nl * 16u;   // chunks 2h, 2h+1
+    const uint32_t sz_off = SC::kXBytes + kStageWBytes + (uint32_t)nl * 4u;
+    const uint32_t a_addr = lane_base + kTmemABase + h * 32;
+    const uint32_t bar_full_a = bar(BAR_FULL_A + h), bar_empty_a = bar(BAR_EMPTY_A + h);
     RingPos rp{0, 0}, ap{0, 0};
     int seg = 0;
+    FB2_STAMP(0);
     ptx::grid_dependency_wait();          // before the first global write / scratch access
-    for (; !wk.done(); wk.next(upt, p.groups, p.n_tiles), rp.advance(S), ap.advance(kASlots)) {
-      const int st = rp.st, slot = ap.st;
-      const uint32_t apar = ap.par;
-      ptx::mbar_wait(bar(BAR_FULL + st), rp.par);
-      const uint8_t *stage = smem + st * SC::kStride + SC::kXBytes;
-      const uint32_t sz = reinterpret_cast<const uint32_t *>(stage + kStageWBytes)[nl];
-      const uint4 w0 = *reinterpret_cast<const uint4 *>(stage + (size_t)(2 * h) * 2048 + nl * 16);
-      const uint4 w1 = *reinterpret_cast<const uint4 *>(stage + (size_t)(2 * h + 1) * 2048 + nl * 16);
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(BAR_EMPTY + st));     // weights are in registers now
+    SegIter si;
+    si.init(u0, u1, upt, n_tiles);
+    Seg sg;
+    while (si.next(sg, upt, n_tiles)) {
+#pragma unroll 1
+      for (int n = sg.r1 - sg.r0; n > 0; n--, rp.advance(S), ap.advance(kASlots)) {
+        const uint32_t stage_addr = smem_base + rp.st * SC::kStride;
+        ptx::mbar_wait(bar(BAR_FULL + rp.st), rp.par);
+        const uint32_t sz = ptx::lds32(stage_addr + sz_off);
+        const uint4 w0 = ptx::lds128(stage_addr + w_off);
+        const uint4 w1 = ptx::lds128(stage_addr + w_off + 2048u);
 
-      const __half s = __ushort_as_half((unsigned short)(sz & 0xFFFF));
-      const __half zl = __ushort_as_half((unsigned short)(sz >> 16));   // 1024 + z
-      const __half2 s2 = __half2half2(s);
-      const __half2 zlo = __half2half2(zl);
-      const __half2 zhi = __hsub2(__float2half2_rn(960.0f), zlo);       // -(64 + z), exact
+        const __half s = __ushort_as_half((unsigned short)(sz & 0xFFFF));
+        const __half zl = __ushort_as_half((unsigned short)(sz >> 16));   // 1024 + z
+        const __half2 s2 = __half2half2(s);
+        const __half2 zlo = __half2half2(zl);
+        const __half2 zhi = __hsub2(__float2half2_rn(960.0f), zlo);       // -(64 + z), exact
 
-      uint32_t r0[16], r1[16];
-      dequant_word(w0.x, zlo, zhi, s2, r0 + 0);
-      dequant_word(w0.y, zlo, zhi, s2, r0 + 4);
-      dequant_word(w0.z, zlo, zhi, s2, r0 + 8);
-      dequant_word(w0.w, zlo, zhi, s2, r0 + 12);
-      dequant_word(w1.x, zlo, zhi, s2, r1 + 0);
-      dequant_word(w1.y, zlo, zhi, s2, r1 + 4);
-      dequant_word(w1.z, zlo, zhi, s2, r1 + 8);
-      dequant_word(w1.w, zlo, zhi, s2, r1 + 12);
+        uint32_t r0[16], r1[16];
+        dequant_word(w0.x, zlo, zhi, s2, r0 + 0);
+        dequant_word(w0.y, zlo, zhi, s2, r0 + 4);
+        dequant_word(w0.z, zlo, zhi, s2, r0 + 8);
+        dequant_word(w0.w, zlo, zhi, s2, r0 + 12);
+        dequant_word(w1.x, zlo, zhi, s2, r1 + 0);
+        dequant_word(w1.y, zlo, zhi, s2, r1 + 4);
+        dequant_word(w1.z, zlo, zhi, s2, r1 + 8);
+        dequant_word(w1.w, zlo, zhi, s2, r1 + 12);
+        // the packed words have been consumed (not merely requested): release the stage
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(BAR_EMPTY + rp.st));
 
-      ptx::mbar_wait(bar(BAR_EMPTY_A + slot * 2 + h), apar ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t ta = lane_base + kTmemABase + slot * 64 + h * 32;
-      ptx::tmem_st_x16(ta, r0);
-      ptx::tmem_st_x16(ta + 16, r1);
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(BAR_FULL_A + slot * 2 + h));
-
-      if (!wk.seg_last(upt)) continue;
+        ptx::mbar_wait(bar_empty_a + ap.st * 16, ap.par ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t ta = a_addr + ap.st * 64;
+        ptx::tmem_st_x16(ta, r0);
+        ptx::tmem_st_x16(ta + 16, r1);
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_full_a + ap.st * 16);
+      }
 
       // ------------------------------------------------ epilogue of this tile segment
-      const int r_begin = wk.seg_r0, r_end = wk.r + 1;          // [r_begin, r_end) of [0, upt)
-      const int blk = wk.blk, tile = wk.tile, tau = wk.blk * p.n_tiles + wk.tile;
+      const int r_begin = sg.r0, r_end = sg.r1;                  // [r_begin, r_end) of [0, upt)
+      const int blk = sg.blk, tile = sg.tile, tau = sg.blk * n_tiles + sg.tile;
+      FB2_STAMP(2);
       ptx::mbar_wait(bar(BAR_ACC), seg & 1);
+      FB2_STAMP(3);
       seg++;
       ptx::tc_fence_after();
       float v[NACC][HALF];
 #pragma unroll
       for (int a = 0; a < NACC; a++) {
-        const bool touched = r_begin < (a + 1) * p.groups && r_end > a * p.groups;   // CTA-uniform
+        const bool touched = r_begin < (a + 1) * groups && r_end > a * groups;   // CTA-uniform
         if (touched) {
           load_acc<NB>(lane_base + a * NB + h * HALF, v[a]);
         } else {
@@ -432,25 +484,30 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       } else {
         // partial tile: fp32 partial, last arriver reduces in contributor order
         constexpr int kPart = NACC * NB * kTileN;
-        const int pslot = wk.seg_at_start ? 0 : 1;
+        const int pslot = sg.at_start ? 0 : 1;
         float *part = p.partials + ((size_t)cta * 2 + pslot) * kPart;
 #pragma unroll
         for (int a = 0; a < NACC; a++)
 #pragma unroll
           for (int j = 0; j < HALF; j++) part[(size_t)(a * NB + h * HALF + j) * kTileN + nl] = v[a][j];
-        __threadfence();
-        ptx::named_bar_sync(1, kDequantWarps * 32);
+        FB2_STAMP(4);
+        ptx::named_bar_sync(1, kDequantWarps * 32);              // all partial stores issued (CTA scope)
         const long long tile_u0 = (long long)tau * upt;
         const int c_first = cta_of_unit(tile_u0, T, G), c_last = cta_of_unit(tile_u0 + upt - 1, T, G);
         if (threadIdx.x == 0) {
+          __threadfence();                                       // cumulative: publishes the CTA's partials
           const int contributors = c_last - c_first + 1;
           const int old = atomicAdd(p.counters + tau, 1);
-          *s_flag = (old == contributors - 1);
-          if (old == contributors - 1) p.counters[tau] = 0;   // self-reset for the next launch
+          const int last = (old == contributors - 1);
+          if (last) {
+            p.counters[tau] = 0;                                 // self-reset for the next launch
+            __threadfence();                                     // acquire side: see the others' partials
+          }
+          *s_flag = last;
         }
         ptx::named_bar_sync(1, kDequantWarps * 32);
+        FB2_STAMP(5);
         if (*s_flag) {
-          __threadfence();
           // Contributors outermost, rows unrolled inside: HALF * NACC independent L2 loads are in
           // flight per step (a row-outer loop would serialise one L2 round trip per addend).
           float sum[NACC][HALF];
@@ -482,8 +539,14 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
           }
         }
         ptx::named_bar_sync(1, kDequantWarps * 32);              // s_flag may be rewritten next segment
+        FB2_STAMP(6);
       }
     }
+#ifdef FB2_TIMELINE
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1)
+      printf("fb2 timeline cta %d units %lld: setup %lld first_full %lld dequant_done %lld acc %lld partial_stored %lld "
+             "atomic_done %lld reduce_done %lld\n", cta, u1 - u0, tl[0], tl[1], tl[2], tl[3], tl[4], tl[5], tl[6]);
+#endif
   }
 
   // -------------------------------------------------------------------------- teardown
@@ -532,7 +595,8 @@ TcPlan make_plan(const WeightRef &w, const RowMap &rows, int epilogue, int sm_co
   pl.nacc = epilogue ? 2 : 1;
   pl.n_tiles = (epilogue ? w.n / 2 : w.n) / kTileN;
   const long long units = (long long)pl.row_blocks * pl.n_tiles * pl.nacc * (w.k / kGroup);
-  const int slots = 2 * (sm_count > 0 ? sm_count : 148);
+  static const int ctas_per_sm = [] { const char *e = getenv("FB2_DEBUG_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
+  const int slots = ctas_per_sm * (sm_count > 0 ? sm_count : 148);
   long long g = units / 2;                       // >= 2 units per CTA: amortise setup / epilogue
   if (g < 1) g = 1;
   pl.grid = (int)(g < slots ? g : slots);
