@@ -78,7 +78,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-i", str(self.index), "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -343,10 +343,13 @@ def run_gpu(args):
     if rank == 0:
         avg_launch_us = ms_step * 1e3 / n_gemms
         achieved = (step_bytes / n_gemms) / (avg_launch_us * 1e-6) / 1e9
-        traffic = None
+        traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = (f"ncu dram read+write of one {tj.get('workload')} launch "
+                            f"(algorithmic {tj.get('algorithmic_bytes_per_launch')} B), {tj.get('source')}")
         line = {
             "metric": "w4a16_gemm_decode_throughput", "value": round(value, 1), "unit": "GB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
@@ -360,8 +363,9 @@ def run_gpu(args):
                        "parallelism": f"tp{world}" if world > 1 else "single"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic, "peak_source": pk["src"],
-                         "kernel": "tc_decode_kernel", "avg_launch_us": round(avg_launch_us, 3),
+                         "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic, "traffic_note": traffic_note,
+                         "peak_source": pk["src"],
+                         "kernel": "tc_gemm_kernel (stream-K, tcgen05)", "avg_launch_us": round(avg_launch_us, 3),
                          "alg_bytes_per_launch": int(step_bytes / n_gemms)},
             "cpu_baseline": cpu, "series_decode": series, "per_shape_M1": per_shape, "prefill": prefill,
             "moe_decode": moe, "build_s": round(build_s, 1), "host_cores": os.cpu_count(),
