@@ -422,7 +422,7 @@ static int run_tc(const WeightRef &w_in, const RowMap &rm, const DispatchTable *
     x = xp;
     w.perm = nullptr;
   }
-  return launch_tc_gemm(w, rm, tbl, x, y, epilogue, sc, sms, stream);
+  return launch_tc_gemm(w, rm, tbl, x, x_rows, y, epilogue, sc, sms, stream);
 }
 
 // Registry of live weights per device so that fb2_pregrow_scratch can size the pool for

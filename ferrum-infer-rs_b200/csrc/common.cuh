@@ -139,8 +139,9 @@ bool tc_supported(const WeightRef &w);
 void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count,
                      size_t *partial_bytes, size_t *counters);
 // tbl != nullptr  <=>  rows.mode == ROWS_DISPATCH
+// x_rows: rows of x that may be addressed (bounds of the activation tensor map)
 int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, const __half *x,
-                   __half *y, int epilogue, const TcScratch &scratch, int sm_count,
+                   size_t x_rows, __half *y, int epilogue, const TcScratch &scratch, int sm_count,
                    cudaStream_t stream);
 const char *tc_kernel_name(const WeightRef &w, size_t m);
 

@@ -37,7 +37,9 @@
 // Programmatic dependent launch: the kernel prefetches its first weight stages (which depend
 // on no earlier kernel) before griddepcontrol.wait, so in a chain of GEMMs the weight stream
 // of GEMM i+1 starts while GEMM i drains.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -53,14 +55,22 @@ constexpr int kDequantWarps = 8;
 constexpr int kWarpTma = kDequantWarps;             // 8
 constexpr int kWarpMma = kDequantWarps + 1;         // 9
 constexpr int kThreads = (kDequantWarps + 2) * 32;  // 320
-constexpr int kTmemCols = 256;                      // [0,128) accumulators, [128,256) A ring
-constexpr int kTmemABase = 128;
-constexpr int kASlots = 2;                          // A ring: slots of one 128-k group (64 columns)
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 108 * 1024;             // per CTA (two CTAs per SM)
+constexpr int kMaxASlots = 4;
 
+// Two resource classes.  NB <= 64 ("decode"): two CTAs per SM, 256 TMEM columns each
+// ([0,128) accumulators, [128,256) a 2-slot A ring).  NB >= 128 ("prefill"): one CTA per SM,
+// all 512 TMEM columns ([0,256) accumulator, [256,512) a 4-slot A ring) and all shared memory:
+// one dequantised weight stage then feeds a 128 x NB x 128 MMA block (NB/2 cycles per MMA), so the
+// tensor pipe, not the int4->fp16 conversion, is the busy unit.
 template <int NB>
 struct StageCfg {
+  static constexpr bool kWide = NB >= 128;
+  static constexpr int kCtasPerSm = kWide ? 1 : 2;
+  static constexpr int kTmemCols = kWide ? 512 : 256;
+  static constexpr int kTmemABase = kWide ? 256 : 128;
+  static constexpr int kASlots = kWide ? 4 : 2;                               // slots of one 128-k group (64 columns)
+  static constexpr int kSmemBudget = kWide ? 225 * 1024 : 108 * 1024;         // per CTA
   static constexpr int kXBytes = NB * 256;                                    // [2 atoms][NB][128 B]
   static constexpr int kStride = (kXBytes + kStageBytes + 1023) & ~1023;      // x first (1024-aligned)
   static constexpr int kStagesRaw = (kSmemBudget - 1024) / kStride;
@@ -79,11 +89,12 @@ struct TcParams {
   int groups;             // K / 128
   int tiles_per_expert;   // ld / 128
   int ld_out;             // output row stride
+  int x_tma;              // activations come through the 2-D tensor map (dense / dispatch rows)
 };
 
 // barrier slots (8 bytes each)
 enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_FULL_A = 2 * kMaxStages,
-       BAR_EMPTY_A = BAR_FULL_A + 2 * kASlots, BAR_ACC = BAR_EMPTY_A + 2 * kASlots,
+       BAR_EMPTY_A = BAR_FULL_A + 2 * kMaxASlots, BAR_ACC = BAR_EMPTY_A + 2 * kMaxASlots,
        BAR_ACC_EMPTY = BAR_ACC + 1, BAR_COUNT = BAR_ACC_EMPTY + 1 };
 static_assert(BAR_COUNT * 8 <= 512, "barrier area too small");
 
@@ -112,6 +123,25 @@ __device__ __forceinline__ void dequant_word(uint32_t q, __half2 zlo, __half2 zh
   out[1] = *reinterpret_cast<uint32_t *>(&v1);
   out[2] = *reinterpret_cast<uint32_t *>(&v2);
   out[3] = *reinterpret_cast<uint32_t *>(&v3);
+}
+
+// CH (8 or 16) consecutive fp32 accumulator columns of this thread's lane
+template <int CH>
+__device__ __forceinline__ void load_acc_chunk(uint32_t taddr, float *v) {
+  static_assert(CH == 8 || CH == 16, "chunk width");
+  if constexpr (CH == 8) {
+    uint32_t r[8];
+    ptx::tmem_ld_x8(taddr, r);
+    ptx::tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+  } else {
+    uint32_t r[16];
+    ptx::tmem_ld_x16(taddr, r);
+    ptx::tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+  }
 }
 
 template <int NB>
@@ -185,9 +215,10 @@ struct RingPos {
 };
 
 template <int NB, bool kSilu>
-__device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *tbl) {
+__device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *tbl, const CUtensorMap *xmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SC = StageCfg<NB>;
+  constexpr int kTmemCols = SC::kTmemCols, kTmemABase = SC::kTmemABase, kASlots = SC::kASlots;
   constexpr int NACC = kSilu ? 2 : 1;
   constexpr int HALF = NB / 2;
   constexpr int S = SC::kStages;
@@ -224,7 +255,8 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   if (warp == kWarpTma) {
     if (lane == 0) {
       for (int i = 0; i < S; i++) {
-        ptx::mbar_init(bar(BAR_FULL + i), 1 + 32);                // expect_tx arrive + 32 cp.async arrives
+        // one arrive.expect_tx by the producer (+ 32 cp.async arrivals when rows are gathered)
+        ptx::mbar_init(bar(BAR_FULL + i), p.x_tma ? 1 : 1 + 32);
         ptx::mbar_init(bar(BAR_EMPTY + i), kDequantWarps + 1);    // 8 warps + the MMA commit
       }
       ptx::mbar_fence_init();
@@ -271,7 +303,9 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
 #pragma unroll 1
           for (int g = g0; g < g1 && pre < S; g++, pre++, src += kStageBytes) {
             if (ptx::elect_one()) {
-              ptx::mbar_arrive_expect_tx(bar(BAR_FULL + pre), kStageBytes);
+              // transaction bytes only: the arrival comes with the activation slice in the main
+              // loop, so the phase cannot complete before the activations are requested too
+              ptx::mbar_expect_tx(bar(BAR_FULL + pre), kStageBytes);
               ptx::bulk_g2s_hint(smem_base + pre * SC::kStride + SC::kXBytes, src, kStageBytes, bar(BAR_FULL + pre), pol);
             }
             __syncwarp();
@@ -293,21 +327,27 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     // ================================================================== producer
     ptx::grid_dependency_wait();
     // rows of the current block: lane i holds row i (and i + 32 for NB == 64)
-    int cur_blk = -1, nchunks = 0, arow0 = -1, arow1 = -1;
+    int cur_blk = -1, nchunks = 0, arow0 = -1, arow1 = -1, row0 = 0;
+    if (p.x_tma && lane == 0) ptx::prefetch_tensormap(xmap);
     RingPos rp{0, 0};
     int it = 0;
     SegIter si;
     si.init(u0, u1, upt, n_tiles);
     Seg sg;
     while (si.next(sg, upt, n_tiles)) {
-      if (sg.blk != cur_blk) {
+      if (sg.blk != cur_blk && p.x_tma) {
         cur_blk = sg.blk;
         int ar, cr;
-        arow0 = (lane < NB && rowmap_resolve(p.rm, tbl, NB, sg.blk, lane, ar, cr)) ? ar : -1;
+        rowmap_resolve(p.rm, tbl, NB, sg.blk, 0, ar, cr);        // dense / dispatch: rows are contiguous
+        row0 = ar;
+      } else if (sg.blk != cur_blk) {
+        cur_blk = sg.blk;
+        int ar, cr;
+        arow0 = (lane < NB && lane < 32 && rowmap_resolve(p.rm, tbl, NB, sg.blk, lane, ar, cr)) ? ar : -1;
         // valid rows form a prefix of the block (moe_align_block_size puts real ids first)
         int nvalid = __popc(__ballot_sync(0xffffffffu, arow0 >= 0));
         if (NB > 32) {
-          arow1 = rowmap_resolve(p.rm, tbl, NB, sg.blk, lane + 32, ar, cr) ? ar : -1;
+          arow1 = (lane + 32 < NB && rowmap_resolve(p.rm, tbl, NB, sg.blk, lane + 32, ar, cr)) ? ar : -1;
           nvalid += __popc(__ballot_sync(0xffffffffu, arow1 >= 0));
         }
         nchunks = nvalid * 16;
@@ -322,26 +362,32 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         for (int g = g0; g < g1; g++, it++, wsrc += kStageBytes, xg += kGroup, rp.advance(S)) {
           const uint32_t stage_addr = smem_base + rp.st * SC::kStride;
           const uint32_t full = bar(BAR_FULL + rp.st);
-          if (it >= pre) {
-            ptx::mbar_wait(bar(BAR_EMPTY + rp.st), rp.par ^ 1u);
-            if (ptx::elect_one()) {
-              ptx::mbar_arrive_expect_tx(full, kStageBytes);
-              ptx::bulk_g2s_hint(stage_addr + SC::kXBytes, wsrc, kStageBytes, full, pol);
-            }
-            __syncwarp();
-          }
-          // activation slice: rows [0, nvalid) x 128 k, 16 chunks of 16 B per row
-          for (int ch0 = 0; ch0 < nchunks; ch0 += 32) {           // warp-uniform trip count
-            const int ch = ch0 + lane;
-            const int i = ch >> 4, c8 = ch & 15;
-            const int ar = __shfl_sync(0xffffffffu, (NB > 32 && i >= 32) ? arow1 : arow0, i & 31);
-            if (ch < nchunks) {
-              const uint32_t dst = stage_addr + (uint32_t)(c8 >> 3) * (NB * 128) + (uint32_t)i * 128 +
-                                   (uint32_t)(((c8 & 7) ^ (i & 7)) << 4);
-              ptx::cp_async_16(dst, xg + (size_t)ar * p.w.k + c8 * 8);
+          if (it >= pre) ptx::mbar_wait(bar(BAR_EMPTY + rp.st), rp.par ^ 1u);
+          if (ptx::elect_one()) {
+            const uint32_t tx = (it >= pre ? (uint32_t)kStageBytes : 0u) + (p.x_tma ? (uint32_t)SC::kXBytes : 0u);
+            ptx::mbar_arrive_expect_tx(full, tx);
+            if (it >= pre) ptx::bulk_g2s_hint(stage_addr + SC::kXBytes, wsrc, kStageBytes, full, pol);
+            if (p.x_tma) {
+              // [NB rows x 64 k] boxes, hardware 128B swizzle; rows past the tensor end read as zero
+              ptx::tma_load_2d(stage_addr, xmap, g * kGroup, row0, full);
+              ptx::tma_load_2d(stage_addr + NB * 128, xmap, g * kGroup + 64, row0, full);
             }
           }
-          ptx::cp_async_mbar_arrive_noinc(full);
+          __syncwarp();
+          if (!p.x_tma) {
+            // gathered activation slice: rows [0, nvalid) x 128 k, 16 chunks of 16 B per row
+            for (int ch0 = 0; ch0 < nchunks; ch0 += 32) {         // warp-uniform trip count
+              const int ch = ch0 + lane;
+              const int i = ch >> 4, c8 = ch & 15;
+              const int ar = __shfl_sync(0xffffffffu, (NB > 32 && i >= 32) ? arow1 : arow0, i & 31);
+              if (ch < nchunks) {
+                const uint32_t dst = stage_addr + (uint32_t)(c8 >> 3) * (NB * 128) + (uint32_t)i * 128 +
+                                     (uint32_t)(((c8 & 7) ^ (i & 7)) << 4);
+                ptx::cp_async_16(dst, xg + (size_t)ar * p.w.k + c8 * 8);
+              }
+            }
+            ptx::cp_async_mbar_arrive_noinc(full);
+          }
         }
       }
     }
@@ -456,40 +502,49 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       FB2_STAMP(3);
       seg++;
       ptx::tc_fence_after();
-      float v[NACC][HALF];
+      // The accumulator is read in chunks of CH columns (activation rows) so that the same code
+      // serves NB = 16 ... 256 without holding NB/2 floats per thread.
+      constexpr int CH = HALF < 16 ? HALF : 16;
+      constexpr int NCH = HALF / CH;
+      constexpr int kPart = NACC * NB * kTileN;
+      const int col = tile * kTileN + nl;
+      const float bias = (!kSilu && p.w.bias) ? p.w.bias[col] : 0.0f;
+      const bool whole = (r_begin == 0 && r_end == upt);         // this CTA covered the whole tile
+      float *part = p.partials + ((size_t)cta * 2 + (sg.at_start ? 0 : 1)) * kPart;
+#pragma unroll 1
+      for (int ch = 0; ch < NCH; ch++) {
+        float v[NACC][CH];
 #pragma unroll
-      for (int a = 0; a < NACC; a++) {
-        const bool touched = r_begin < (a + 1) * groups && r_end > a * groups;   // CTA-uniform
-        if (touched) {
-          load_acc<NB>(lane_base + a * NB + h * HALF, v[a]);
+        for (int a = 0; a < NACC; a++) {
+          const bool touched = r_begin < (a + 1) * groups && r_end > a * groups;   // CTA-uniform
+          if (touched) {
+            load_acc_chunk<CH>(lane_base + a * NB + h * HALF + ch * CH, v[a]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; j++) v[a][j] = 0.0f;
+          }
+        }
+        if (whole) {
+#pragma unroll
+          for (int j = 0; j < CH; j++) {
+            int ar, cr;
+            if (!rowmap_resolve(p.rm, tbl, NB, blk, h * HALF + ch * CH + j, ar, cr)) continue;
+            const float o = kSilu ? silu_mul(v[0][j], v[NACC - 1][j]) : v[0][j] + bias;
+            p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
+          }
         } else {
 #pragma unroll
-          for (int j = 0; j < HALF; j++) v[a][j] = 0.0f;
+          for (int a = 0; a < NACC; a++)
+#pragma unroll
+            for (int j = 0; j < CH; j++)
+              part[(size_t)(a * NB + h * HALF + ch * CH + j) * kTileN + nl] = v[a][j];
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar(BAR_ACC_EMPTY));      // accumulators may be overwritten
-      const int col = tile * kTileN + nl;
-      const float bias = (!kSilu && p.w.bias) ? p.w.bias[col] : 0.0f;
-      if (r_begin == 0 && r_end == upt) {
-        // this CTA covered the whole tile: direct store
-#pragma unroll
-        for (int j = 0; j < HALF; j++) {
-          int ar, cr;
-          if (!rowmap_resolve(p.rm, tbl, NB, blk, h * HALF + j, ar, cr)) continue;
-          const float o = kSilu ? silu_mul(v[0][j], v[NACC - 1][j]) : v[0][j] + bias;
-          p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
-        }
-      } else {
-        // partial tile: fp32 partial, last arriver reduces in contributor order
-        constexpr int kPart = NACC * NB * kTileN;
-        const int pslot = sg.at_start ? 0 : 1;
-        float *part = p.partials + ((size_t)cta * 2 + pslot) * kPart;
-#pragma unroll
-        for (int a = 0; a < NACC; a++)
-#pragma unroll
-          for (int j = 0; j < HALF; j++) part[(size_t)(a * NB + h * HALF + j) * kTileN + nl] = v[a][j];
+      if (!whole) {
+        // partial tile: fp32 partial stored above; last arriver reduces in contributor order
         FB2_STAMP(4);
         ptx::named_bar_sync(1, kDequantWarps * 32);              // all partial stores issued (CTA scope)
         const long long tile_u0 = (long long)tau * upt;
@@ -508,34 +563,38 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         ptx::named_bar_sync(1, kDequantWarps * 32);
         FB2_STAMP(5);
         if (*s_flag) {
-          // Contributors outermost, rows unrolled inside: HALF * NACC independent L2 loads are in
+          // Contributors outermost, rows unrolled inside: CH * NACC independent L2 loads are in
           // flight per step (a row-outer loop would serialise one L2 round trip per addend).
-          float sum[NACC][HALF];
-#pragma unroll
-          for (int a = 0; a < NACC; a++)
-#pragma unroll
-            for (int j = 0; j < HALF; j++) sum[a][j] = 0.0f;
-          const float *src = p.partials + ((size_t)c_first * 2 + (range_start(c_first, T, G) >= tile_u0 ? 0 : 1)) * kPart +
-                             (size_t)(h * HALF) * kTileN + nl;
-          for (int c = c_first; c <= c_last; c++) {
-            float t[NACC][HALF];
+          const size_t first_off = ((size_t)c_first * 2 + (range_start(c_first, T, G) >= tile_u0 ? 0 : 1)) * kPart;
+#pragma unroll 1
+          for (int ch = 0; ch < NCH; ch++) {
+            float sum[NACC][CH];
 #pragma unroll
             for (int a = 0; a < NACC; a++)
 #pragma unroll
-              for (int j = 0; j < HALF; j++) t[a][j] = __ldcg(src + (size_t)(a * NB + j) * kTileN);
+              for (int j = 0; j < CH; j++) sum[a][j] = 0.0f;
+            const size_t row_off = (size_t)(h * HALF + ch * CH) * kTileN + nl;
+            const float *src = p.partials + first_off + row_off;
+            for (int c = c_first; c <= c_last; c++) {
+              float t[NACC][CH];
 #pragma unroll
-            for (int a = 0; a < NACC; a++)
+              for (int a = 0; a < NACC; a++)
 #pragma unroll
-              for (int j = 0; j < HALF; j++) sum[a][j] += t[a][j];
-            // every contributor after the first starts inside the tile -> its slot 0
-            src = p.partials + ((size_t)(c + 1) * 2) * kPart + (size_t)(h * HALF) * kTileN + nl;
-          }
+                for (int j = 0; j < CH; j++) t[a][j] = __ldcg(src + (size_t)(a * NB + j) * kTileN);
 #pragma unroll
-          for (int j = 0; j < HALF; j++) {
-            int ar, cr;
-            if (!rowmap_resolve(p.rm, tbl, NB, blk, h * HALF + j, ar, cr)) continue;
-            const float o = kSilu ? silu_mul(sum[0][j], sum[NACC - 1][j]) : sum[0][j] + bias;
-            p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
+              for (int a = 0; a < NACC; a++)
+#pragma unroll
+                for (int j = 0; j < CH; j++) sum[a][j] += t[a][j];
+              // every contributor after the first starts inside the tile -> its slot 0
+              src = p.partials + ((size_t)(c + 1) * 2) * kPart + row_off;
+            }
+#pragma unroll
+            for (int j = 0; j < CH; j++) {
+              int ar, cr;
+              if (!rowmap_resolve(p.rm, tbl, NB, blk, h * HALF + ch * CH + j, ar, cr)) continue;
+              const float o = kSilu ? silu_mul(sum[0][j], sum[NACC - 1][j]) : sum[0][j] + bias;
+              p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
+            }
           }
         }
         ptx::named_bar_sync(1, kDequantWarps * 32);              // s_flag may be rewritten next segment
@@ -556,15 +615,17 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
 }
 
 template <int NB, bool kSilu>
-__global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kThreads, StageCfg<NB>::kCtasPerSm)
+tc_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
   ptx::launch_dependents();
-  tc_body<NB, kSilu>(p, nullptr);
+  tc_body<NB, kSilu>(p, nullptr, &xmap);
 }
 template <int NB>
-__global__ void __launch_bounds__(kThreads, 2)
-tc_gemm_dispatch_kernel(const TcParams p, const __grid_constant__ DispatchTable tbl) {
+__global__ void __launch_bounds__(kThreads, StageCfg<NB>::kCtasPerSm)
+tc_gemm_dispatch_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap,
+                        const __grid_constant__ DispatchTable tbl) {
   ptx::launch_dependents();
-  tc_body<NB, false>(p, &tbl);
+  tc_body<NB, false>(p, &tbl, &xmap);
 }
 
 // ------------------------------------------------------------------------ host planning
@@ -574,39 +635,85 @@ struct TcPlan {
   uint32_t smem;
 };
 
-int pick_nb(int rows_per_block) { return rows_per_block <= 16 ? 16 : rows_per_block <= 32 ? 32 : 64; }
+int pick_nb(int rows_per_block, bool allow_wide) {
+  if (rows_per_block <= 16) return 16;
+  if (rows_per_block <= 32) return 32;
+  if (rows_per_block <= 64 || !allow_wide) return 64;
+  return rows_per_block <= 128 ? 128 : 256;
+}
 
-void plan_rows(const RowMap &rows, int &nb, int &row_blocks) {
+void plan_rows(const RowMap &rows, int epilogue, int &nb, int &row_blocks) {
   if (rows.mode == ROWS_DENSE) {
-    nb = pick_nb(rows.m);
+    nb = pick_nb(rows.m, !epilogue);
     row_blocks = (rows.m + nb - 1) / nb;
   } else if (rows.mode == ROWS_DISPATCH) {
     nb = rows.block;           // host pre-split the entries into chunks of <= rows.block rows
     row_blocks = rows.num_dispatch;
   } else {
-    nb = pick_nb(rows.block);
+    nb = pick_nb(rows.block, false);
     row_blocks = rows.max_blocks;
   }
 }
 
+template <int NB> constexpr uint32_t smem_of() { return (uint32_t)StageCfg<NB>::kSmemBytes; }
+
 TcPlan make_plan(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count) {
   TcPlan pl{};
-  plan_rows(rows, pl.nb, pl.row_blocks);
+  plan_rows(rows, epilogue, pl.nb, pl.row_blocks);
   pl.nacc = epilogue ? 2 : 1;
   pl.n_tiles = (epilogue ? w.n / 2 : w.n) / kTileN;
   const long long units = (long long)pl.row_blocks * pl.n_tiles * pl.nacc * (w.k / kGroup);
-  static const int ctas_per_sm = [] { const char *e = getenv("FB2_DEBUG_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
-  const int slots = ctas_per_sm * (sm_count > 0 ? sm_count : 148);
+  static const int ctas_per_sm_dbg = [] { const char *e = getenv("FB2_DEBUG_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  const int per_sm = ctas_per_sm_dbg ? ctas_per_sm_dbg : (pl.nb >= 128 ? 1 : 2);
+  const int slots = per_sm * (sm_count > 0 ? sm_count : 148);
   long long g = units / 2;                       // >= 2 units per CTA: amortise setup / epilogue
   if (g < 1) g = 1;
   pl.grid = (int)(g < slots ? g : slots);
   pl.partial_floats = (size_t)pl.grid * 2 * pl.nacc * pl.nb * kTileN;
   pl.counters = (size_t)pl.row_blocks * pl.n_tiles;
-  pl.smem = pl.nb == 16 ? StageCfg<16>::kSmemBytes : pl.nb == 32 ? StageCfg<32>::kSmemBytes : StageCfg<64>::kSmemBytes;
+  pl.smem = pl.nb == 16 ? smem_of<16>() : pl.nb == 32 ? smem_of<32>() : pl.nb == 64 ? smem_of<64>()
+            : pl.nb == 128 ? smem_of<128>() : smem_of<256>();
   return pl;
 }
 
-int launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, const TcPlan &pl, cudaStream_t stream) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+// x viewed as a [rows, K] fp16 tensor; box = 64 k (128 B, SWIZZLE_128B) x nb rows; OOB rows -> 0.
+int make_x_tensor_map(CUtensorMap *map, const __half *x, size_t rows, size_t k, int nb) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return FB2_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)k * sizeof(__half)};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)nb};
+  const cuuint32_t estride[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half *>(x), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for x [%zu, %zu], box rows %d", (int)r, rows, k, nb);
+    return FB2_ERR_CUDA;
+  }
+  return FB2_OK;
+}
+
+void launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, const TcPlan &pl, cudaStream_t stream) {
   cfg = cudaLaunchConfig_t{};
   cfg.gridDim = dim3((unsigned)pl.grid);
   cfg.blockDim = dim3(kThreads);
@@ -616,25 +723,25 @@ int launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, const TcPlan 
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return FB2_OK;
 }
 
 template <int NB, bool kSilu>
-int launch_plain(const TcPlan &pl, cudaStream_t stream, const TcParams &p) {
+int launch_plain(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
   FB2_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<NB, kSilu>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   launch_cfg(cfg, attr, pl, stream);
-  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NB, kSilu>, p));
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NB, kSilu>, p, xmap));
   return FB2_OK;
 }
 template <int NB>
-int launch_dispatch(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const DispatchTable &tbl) {
+int launch_dispatch(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap,
+                    const DispatchTable &tbl) {
   FB2_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_dispatch_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   launch_cfg(cfg, attr, pl, stream);
-  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_dispatch_kernel<NB>, p, tbl));
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_dispatch_kernel<NB>, p, xmap, tbl));
   return FB2_OK;
 }
 
@@ -646,8 +753,8 @@ bool tc_supported(const WeightRef &w) {
 }
 
 const char *tc_kernel_name(const WeightRef &w, size_t m) {
-  (void)m;
-  return tc_supported(w) ? "tc-streamk" : "generic";
+  if (!tc_supported(w)) return "generic";
+  return m > 64 ? "tc-streamk-prefill" : "tc-streamk";
 }
 
 void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count,
@@ -655,7 +762,7 @@ void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int s
   *partial_bytes = 0;
   *counters = 0;
   int nb, row_blocks;
-  plan_rows(rows, nb, row_blocks);
+  plan_rows(rows, epilogue, nb, row_blocks);
   if (row_blocks <= 0) return;
   TcPlan pl = make_plan(w, rows, epilogue, sm_count);
   *partial_bytes = pl.partial_floats * sizeof(float);
@@ -663,14 +770,14 @@ void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int s
 }
 
 int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, const __half *x,
-                   __half *y, int epilogue, const TcScratch &scratch, int sm_count,
+                   size_t x_rows, __half *y, int epilogue, const TcScratch &scratch, int sm_count,
                    cudaStream_t stream) {
   if (!tc_supported(w)) {
     set_error("tensor-core path needs the tiled weight format (K,N multiples of 128, group 128)");
     return FB2_ERR_UNSUPPORTED;
   }
   int nb, row_blocks;
-  plan_rows(rows, nb, row_blocks);
+  plan_rows(rows, epilogue, nb, row_blocks);
   if (row_blocks <= 0) return FB2_OK;
   if (epilogue && (w.n / 2) % kTileN) {
     set_error("SiLU epilogue needs n_per_expert/2 to be a multiple of 128");
@@ -698,17 +805,32 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   p.groups = w.k / kGroup;
   p.tiles_per_expert = w.ld / kTileN;
   p.ld_out = epilogue ? w.n / 2 : w.n;
+  // Rows that are contiguous in x (dense batches, dispatch entries) come through a 2-D TMA tensor
+  // map: one instruction per [NB x 64] box instead of NB*16 cp.async.  Routed rows are gathered.
+  CUtensorMap xmap;
+  memset(&xmap, 0, sizeof(xmap));
+  p.x_tma = 0;
+  if (rows.mode != ROWS_ROUTED && x_rows > 0 && ((uintptr_t)x % 16) == 0) {
+    int rc = make_x_tensor_map(&xmap, x, x_rows, (size_t)w.k, nb);
+    if (rc) return rc;
+    p.x_tma = 1;
+  } else if (nb > 64) {
+    set_error("internal: wide row blocks need the tensor-map path");
+    return FB2_ERR_ARG;
+  }
 
   int rc;
   if (tbl) {
-    rc = nb == 16 ? launch_dispatch<16>(pl, stream, p, *tbl)
-         : nb == 32 ? launch_dispatch<32>(pl, stream, p, *tbl) : launch_dispatch<64>(pl, stream, p, *tbl);
+    rc = nb == 16 ? launch_dispatch<16>(pl, stream, p, xmap, *tbl)
+         : nb == 32 ? launch_dispatch<32>(pl, stream, p, xmap, *tbl) : launch_dispatch<64>(pl, stream, p, xmap, *tbl);
   } else if (epilogue) {
-    rc = nb == 16 ? launch_plain<16, true>(pl, stream, p)
-         : nb == 32 ? launch_plain<32, true>(pl, stream, p) : launch_plain<64, true>(pl, stream, p);
+    rc = nb == 16 ? launch_plain<16, true>(pl, stream, p, xmap)
+         : nb == 32 ? launch_plain<32, true>(pl, stream, p, xmap) : launch_plain<64, true>(pl, stream, p, xmap);
   } else {
-    rc = nb == 16 ? launch_plain<16, false>(pl, stream, p)
-         : nb == 32 ? launch_plain<32, false>(pl, stream, p) : launch_plain<64, false>(pl, stream, p);
+    rc = nb == 16 ? launch_plain<16, false>(pl, stream, p, xmap)
+         : nb == 32 ? launch_plain<32, false>(pl, stream, p, xmap)
+         : nb == 64 ? launch_plain<64, false>(pl, stream, p, xmap)
+         : nb == 128 ? launch_plain<128, false>(pl, stream, p, xmap) : launch_plain<256, false>(pl, stream, p, xmap);
   }
   if (rc) return rc;
   count_launch();
