@@ -370,10 +370,12 @@ def run_gpu(args):
             "cpu_baseline": cpu, "series_decode": series, "per_shape_M1": per_shape, "prefill": prefill,
             "moe_decode": moe, "build_s": round(build_s, 1), "host_cores": os.cpu_count(),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+        # leave without the NCCL / CUDA-graph teardown (it can block when graphs hold collectives)
+        barrier(world)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def run_moe(args, fb2, par, rank, world, local, pk):
@@ -382,6 +384,8 @@ def run_moe(args, fb2, par, rank, world, local, pk):
     import torch
     H, I, E, K = QWEN3["hidden"], QWEN3["inter"], QWEN3["experts"], QWEN3["top_k"]
     layers = args.moe_layers
+    if world > 1:
+        args.moe_batches = [b for b in (32, 64, 128, 256) if b % world == 0]     # BASELINE.json configs[3]
     dev = f"cuda:{local}"
     wrng = np.random.default_rng(4242)
     gi_gu = gi_dn = None
@@ -401,36 +405,28 @@ def run_moe(args, fb2, par, rank, world, local, pk):
         if world == 1:
             ffns.append(fb2.moe.MoeFfn(gst, dst, K, True, max_batch=max(args.moe_batches)))
         else:
-            ffns.append(par.ExpertParallelFfn(gst, dst, K, True, max(args.moe_batches), E, rank, world))
-    fb2.pregrow_scratch(local, max(args.moe_batches) * K)
+            ffns.append(par.ExpertParallelFfn(gst, dst, K, True, max(args.moe_batches) // world, E, rank, world))
+    fb2.pregrow_scratch(local, max(args.moe_batches) * K)          # EP: world * (B/world * K) received rows
     out = {}
     for B in args.moe_batches:
-        x = torch.randn(B, H, device=dev).clamp_(-1, 1).half()
-        lg = (torch.rand(B, E, device=dev) * 4 - 2).half()
-        if world > 1:
-            import torch.distributed as dist
-            dist.broadcast(x, 0); dist.broadcast(lg, 0)
-        y = torch.empty(B, H, device=dev, dtype=torch.float16)
+        if B % world:
+            continue
+        b_loc = B // world                                        # EP: tokens are batch-sharded
+        torch.manual_seed(1000 + B)                               # same global batch on every rank
+        xg = torch.randn(B, H, device=dev).clamp_(-1, 1).half()
+        lgg = (torch.rand(B, E, device=dev) * 4 - 2).half()
+        x = xg[rank * b_loc:(rank + 1) * b_loc].contiguous()
+        lg = lgg[rank * b_loc:(rank + 1) * b_loc].contiguous()
+        y = torch.empty(b_loc, H, device=dev, dtype=torch.float16)
 
         def fn():
             for f in ffns:
                 f.forward(x, lg, y)
-        if world == 1:
-            g = capture(fn)
-            t = time_graph(g, 5, 3, world) / 5
-        else:
-            for _ in range(3):
-                fn()
-            barrier(world)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(5):
-                fn()
-            e1.record()
-            barrier(world)
-            t = max_over_ranks(e0.elapsed_time(e1), world) / 5
+        g = capture(fn)              # NCCL all-to-alls are captured with the kernels (no host work per layer)
+        t = time_graph(g, 5, 3, world) / 5
+        del g
         t_layer = t / layers                                     # ms
-        ids = torch.topk(lg.float(), K, dim=1).indices
+        ids = torch.topk(lgg.float(), K, dim=1).indices
         uniq = int(torch.unique(ids).numel())
         bytes_layer = uniq * (1634304 + 817152) + B * H * 2 * 2
         out[f"B={B}"] = {"tok_s_ffn_only": round(B / (QWEN3["layers"] * t_layer * 1e-3), 1),

@@ -116,3 +116,141 @@ def all_reduce_(t):
     import torch.distributed as dist
     dist.all_reduce(t)
     return t
+
+
+# ------------------------------------------------------------------------------------------
+# Tensor-parallel linear: a sharded GptqLinear + the collective that completes it.
+# ------------------------------------------------------------------------------------------
+class TensorParallelLinear:
+    """One projection of a tensor-parallel layer (tensor_parallel.rs:171-195).
+
+    column-parallel: forward(x_full [M, K]) -> local [M, N/R] slice (no exchange: it feeds the local
+    row-parallel shard).  row-parallel: forward(x_local [M, K/R]) -> partial [M, N], then one sum
+    all-reduce (nccl_comm.rs:40); `x_cols` tells which columns of the full activation this rank
+    consumes (for act-order layers that is perm[rank chunk], see row_shard())."""
+
+    def __init__(self, name, qweight, scales, qzeros, g_idx, bias, bits, group, k, n, rank, world, device=0,
+                 qkv_segments=None):
+        from .gptq import GptqLinear
+        self.name, self.rank, self.world = name, rank, world
+        self.row_parallel = name in ROW_PARALLEL
+        self.x_cols = None
+        if world == 1:
+            qw, sc, qz, gi, kl, nl = qweight, scales, qzeros, g_idx, k, n
+        elif self.row_parallel:
+            qw, sc, qz, gi, kl, self.x_cols = row_shard(qweight, scales, qzeros, g_idx, k, n, group, rank, world)
+            nl = n
+            if bias is not None and rank != 0:
+                bias = None                          # bias is added once, by rank 0's partial
+        else:
+            qw, sc, qz, gi, kl, nl = shard_gptq(name, qweight, scales, qzeros, g_idx, k, n, group, rank, world,
+                                                qkv_segments)
+            if bias is not None:
+                seg = (list(qkv_segments) if qkv_segments else _default_qkv_segments(n)) if name == "qkv_proj" \
+                    else ([n // 2, n // 2] if name == "gate_up_proj" else [n])
+                cols, off = [], 0
+                for w in seg:
+                    s = w // world
+                    cols.append(np.arange(off + rank * s, off + (rank + 1) * s))
+                    off += w
+                bias = np.asarray(bias, dtype=np.float32)[np.concatenate(cols)]
+        self.k_local, self.n_local = kl, nl
+        self.linear = GptqLinear.from_raw(qw, sc, qz, gi, bias, bits, group, kl, nl, device=device)
+
+    def forward(self, x, out=None, m=None):
+        y = self.linear.forward(x, out, m)
+        if self.row_parallel and self.world > 1:
+            all_reduce_(y)
+        return y
+
+    __call__ = forward
+
+
+# ------------------------------------------------------------------------------------------
+# Expert parallelism: experts partitioned contiguously over ranks, tokens batch-sharded, one
+# all-to-all dispatch and one all-to-all return per MoE layer (SURVEY.md 8e).  The reference has
+# no EP (is_ep is hard-wired false, backend/cuda/quant.rs:1179); parity is defined against the
+# single-GPU MoE FFN.
+# ------------------------------------------------------------------------------------------
+def ep_plan(ids: np.ndarray, num_experts: int, world: int, capacity: int):
+    """Host (numpy) statement of the dispatch plan, used by the CPU tests: for every (token, k)
+    pair the destination rank, its slot in the fixed-capacity send buffer [world, capacity] and
+    the expert id local to the destination."""
+    ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+    e_loc = num_experts // world
+    dest = ids // e_loc
+    local = ids - dest * e_loc
+    slot = np.zeros_like(ids)
+    counts = np.zeros(world, dtype=np.int64)
+    for p, d in enumerate(dest):                      # (token, k) order == MoeBucketPlan order
+        slot[p] = counts[d]
+        counts[d] += 1
+    assert counts.max(initial=0) <= capacity
+    return dest, slot, local, counts
+
+
+class ExpertParallelFfn:
+    """MoE FFN with the experts of rank r = [r*E/R, (r+1)*E/R).  forward() takes this rank's tokens
+    ([B_loc, H], router logits [B_loc, E]) and returns their outputs.  Fixed-capacity exchange
+    buffers (capacity = B_loc * top_k pairs per peer) keep the whole layer free of host syncs."""
+
+    def __init__(self, gate_up, down, top_k, norm_topk_prob, max_batch, num_experts, rank, world):
+        import torch
+        from . import moe
+        self.moe, self.torch = moe, torch
+        self.gate_up, self.down = gate_up, down
+        self.top_k, self.norm, self.max_batch = top_k, norm_topk_prob, max_batch
+        self.E, self.rank, self.world = num_experts, rank, world
+        self.e_loc = num_experts // world
+        assert gate_up.num_experts() == self.e_loc
+        self.hidden, self.inter = gate_up.k(), gate_up.n_per_expert() // 2
+        self.cap = max_batch * top_k
+        dev = f"cuda:{gate_up.device}"
+        rows = world * self.cap
+        f16, i32 = torch.float16, torch.int32
+        self.send_x = torch.zeros((rows, self.hidden), dtype=f16, device=dev)
+        self.recv_x = torch.zeros((rows, self.hidden), dtype=f16, device=dev)
+        self.send_meta = torch.full((rows,), -1, dtype=i32, device=dev)
+        self.recv_meta = torch.full((rows,), -1, dtype=i32, device=dev)
+        self.act = torch.empty((rows, self.inter), dtype=f16, device=dev)
+        self.down_out = torch.zeros((rows, self.hidden), dtype=f16, device=dev)
+        self.ret = torch.zeros((rows, self.hidden), dtype=f16, device=dev)
+        self.block = 16
+
+    def forward(self, x, router_logits, out=None):
+        torch, moe = self.torch, self.moe
+        import torch.distributed as dist
+        B = x.shape[0]
+        K, R, C = self.top_k, self.world, self.cap
+        if out is None:
+            out = torch.empty((B, self.hidden), dtype=torch.float16, device=x.device)
+        ids, w = moe.route_topk_softmax(router_logits, K, self.norm)            # [B,K]
+        flat = ids.reshape(-1)
+        dest = torch.div(flat, self.e_loc, rounding_mode="floor").to(torch.int32)
+        # counting sort of the pairs by destination rank (deterministic, (token,k) order inside a rank)
+        pbt, pti, offs = moe.moe_build_pairs_by_token(dest, R, K)
+        slot = dest.long() * C + (pbt.long() - offs[:-1].long()[dest.long()])   # position in [R, C]
+        self.send_meta.fill_(-1)
+        self.send_meta[slot] = (flat - dest * self.e_loc)
+        tok = torch.arange(B * K, device=x.device) // K
+        self.send_x[slot] = x[tok]
+        if R > 1:
+            dist.all_to_all_single(self.recv_x, self.send_x)
+            dist.all_to_all_single(self.recv_meta, self.send_meta)
+            rx, rmeta = self.recv_x, self.recv_meta
+        else:
+            rx, rmeta = self.send_x, self.send_meta
+        # local grouped GEMMs over the received rows (row id == position in the receive buffer)
+        rows = R * C
+        s, b, t = moe.moe_align_block_size(rmeta, self.e_loc, self.block, None, pair_ids=True)
+        self.gate_up.gemm_phase_vllm(rx, s, b, t, self.act, rows, self.block, 1, silu=True)
+        self.down.gemm_phase_vllm(self.act, s, b, t, self.down_out, rows, self.block, 1)
+        if R > 1:
+            dist.all_to_all_single(self.ret, self.down_out)
+            ret = self.ret
+        else:
+            ret = self.down_out
+        moe.moe_combine(ret, slot.to(torch.int32).contiguous(), w.reshape(-1).contiguous(), out, B, self.hidden, K)
+        return out
+
+    __call__ = forward

@@ -1,0 +1,95 @@
+"""Multi-GPU parity worker (launched by torchrun from tests/test_multi_gpu.py, one rank per GPU):
+TP row/column-parallel GPTQ linears + all-reduce, and the expert-parallel MoE FFN with all-to-all,
+each against the single-GPU result of the same library (and transitively the CPU oracle)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+
+fb2 = importlib.import_module("ferrum-infer-rs_b200")
+par = importlib.import_module("ferrum-infer-rs_b200.parallel")
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+
+    # ---------------- dense TP: gate_up (column) -> SiLU*up -> down (row) + all-reduce, act-order
+    hidden, inter, g, m = 1024, 2048, 128, 5
+    gu = oracle.make_synthetic(hidden, 2 * inter, g, 0x61, f16_scales=True)
+    dn = oracle.make_synthetic(inter, hidden, g, 0x62, f16_scales=True)
+    gi_gu = oracle.random_balanced_g_idx(hidden, g, 1)
+    gi_dn = oracle.random_balanced_g_idx(inter, g, 2)
+    x = oracle.f16_round(oracle.lcg_f32_array(3, m * hidden, -1.0, 1.0)).reshape(m, hidden)
+    xd = torch.from_numpy(x.astype(np.float16)).to(dev)
+    # single-GPU result
+    l_gu = fb2.GptqLinear.from_raw(gu.qweight, gu.scales, gu.qzeros, gi_gu, None, 4, g, hidden, 2 * inter, device=local)
+    l_dn = fb2.GptqLinear.from_raw(dn.qweight, dn.scales, dn.qzeros, gi_dn, None, 4, g, inter, hidden, device=local)
+    h_full = l_gu.forward(xd)
+    act_full = torch.empty((m, inter), dtype=torch.float16, device=dev)
+    fb2.moe.fused_silu_mul_split(h_full, act_full, m, inter)
+    y_full = l_dn.forward(act_full)
+    # TP: the row-parallel shard's input columns define the column-parallel shard's output order
+    t_dn = par.TensorParallelLinear("down_proj", dn.qweight, dn.scales, dn.qzeros, gi_dn, None, 4, g, inter, hidden,
+                                    rank, world, device=local)
+    cols = np.asarray(t_dn.x_cols)                     # columns of act (== gate/up channel ids) this rank consumes
+    sel = np.concatenate([cols, inter + cols])         # permuted column-parallel gate||up slice
+    qw_c = np.ascontiguousarray(gu.qweight.reshape(hidden // 8, 2 * inter)[:, sel])
+    sc_c = np.ascontiguousarray(gu.scales.reshape(hidden // g, 2 * inter)[:, sel])
+    # qzeros pack 8 columns per word: unpack / select / repack
+    z = gu.qzeros.reshape(hidden // g, 2 * inter // 8).view(np.uint32)
+    zn = ((z[:, :, None] >> (np.arange(8, dtype=np.uint32) * 4)) & 0xF).reshape(hidden // g, 2 * inter)[:, sel]
+    qz_c = (zn.reshape(hidden // g, -1, 8).astype(np.uint32) << (np.arange(8, dtype=np.uint32) * 4)).sum(
+        axis=2, dtype=np.uint32).view(np.int32)
+    t_gu = fb2.GptqLinear.from_raw(qw_c, sc_c, qz_c, gi_gu, None, 4, g, hidden, len(sel), device=local)
+    h_loc = t_gu.forward(xd)
+    act_loc = torch.empty((m, len(cols)), dtype=torch.float16, device=dev)
+    fb2.moe.fused_silu_mul_split(h_loc, act_loc, m, len(cols))
+    y_tp = t_dn.forward(act_loc)
+    torch.cuda.synchronize()
+    rel = (y_tp.float() - y_full.float()).abs().max().item() / y_full.float().abs().max().item()
+    assert rel < 2e-3, f"TP vs single-GPU rel {rel}"
+    # and against the oracle
+    w_gu = oracle.dequant_gptq(gu.qweight, gu.scales, gu.qzeros, gi_gu, 4, g, hidden, 2 * inter)
+    w_dn = oracle.dequant_gptq(dn.qweight, dn.scales, dn.qzeros, gi_dn, 4, g, inter, hidden)
+    ref = oracle.gemm(oracle.f16_round(oracle.silu_mul_split(oracle.f16_round(oracle.gemm(x, w_gu, m, 2 * inter, hidden)), m, inter)),
+                      w_dn, m, hidden, inter)
+    st = oracle.error_stats(y_tp.float().cpu().numpy(), ref)
+    assert st["rel"] < 1e-2, st
+
+    # ---------------- MoE EP: all-to-all dispatch / return vs the single-GPU fused FFN
+    H, I, E, K, B = 512, 256, 8, 2, 4 * world
+    gus = [oracle.make_synthetic(H, 2 * I, g, 0x700 + e, f16_scales=True) for e in range(E)]
+    dns = [oracle.make_synthetic(I, H, g, 0x800 + e, f16_scales=True) for e in range(E)]
+    xs = oracle.f16_round(oracle.lcg_f32_array(9, B * H, -1.0, 1.0)).reshape(B, H)
+    lg = oracle.f16_round(oracle.lcg_f32_array(10, B * E, -2.0, 2.0)).reshape(B, E)
+    mk = lambda parts, k, n: fb2.GptqExpertStack.load_gptq_stacked([p.qweight for p in parts], [p.scales for p in parts],
+                                                                   [p.qzeros for p in parts], None, 4, g, k, n, device=local)
+    full = fb2.moe.MoeFfn(mk(gus, H, 2 * I), mk(dns, I, H), K, True, max_batch=B)
+    y_ref = full.forward(torch.from_numpy(xs.astype(np.float16)).to(dev), torch.from_numpy(lg.astype(np.float16)).to(dev))
+    e_loc = E // world
+    ep = par.ExpertParallelFfn(mk(gus[rank * e_loc:(rank + 1) * e_loc], H, 2 * I), mk(dns[rank * e_loc:(rank + 1) * e_loc], I, H),
+                               K, True, B // world, E, rank, world)
+    b_loc = B // world
+    sl = slice(rank * b_loc, (rank + 1) * b_loc)
+    y_ep = ep.forward(torch.from_numpy(xs[sl].astype(np.float16)).to(dev), torch.from_numpy(lg[sl].astype(np.float16)).to(dev))
+    torch.cuda.synchronize()
+    d = (y_ep.float() - y_ref[sl].float()).abs().max().item() / max(y_ref.float().abs().max().item(), 1e-6)
+    assert d < 2e-3, f"EP vs single-GPU rel {d}"
+    dist.barrier()
+    if rank == 0:
+        print(f"mgpu ok: world={world} tp_rel={rel:.2e} tp_vs_oracle={st['rel']:.2e} ep_rel={d:.2e}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
