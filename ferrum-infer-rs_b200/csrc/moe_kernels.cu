@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(32)
 router_kernel(const __half *__restrict__ logits, int32_t *__restrict__ out_ids,
               float *__restrict__ out_w, int batch, int num_experts, int top_k, int norm) {
   extern __shared__ float probs[];
+  // PDL: let the next kernel start its prologue; wait for the previous kernel's results
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int row = blockIdx.x, lane = threadIdx.x;
   if (row >= batch) return;
   float tmax = -INFINITY;
@@ -114,6 +117,9 @@ build_pairs_kernel(const int32_t *__restrict__ expert_ids, int32_t *__restrict__
                    int32_t *__restrict__ packed_token_idx, int32_t *__restrict__ expert_offsets,
                    int pairs, int num_experts, int top_k) {
   __shared__ int warp_sums[64];
+  // PDL: let the next kernel start its prologue; wait for the previous kernel's results
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int e = blockIdx.x;
   const int per = (pairs + kSortThreads - 1) / kSortThreads;
   const int p0 = min(pairs, (int)threadIdx.x * per), p1 = min(pairs, p0 + per);
@@ -152,6 +158,9 @@ align_block_size_kernel(const int32_t *__restrict__ expert_ids,
   __shared__ int hist[kMaxExperts];
   __shared__ int warp_sums[64];
   __shared__ int s_pad_off, s_unpad_off, s_total_pad;
+  // PDL: let the next kernel start its prologue; wait for the previous kernel's results
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int e = blockIdx.x;
   for (int i = threadIdx.x; i < num_experts; i += kSortThreads) hist[i] = 0;
   __syncthreads();
@@ -203,6 +212,9 @@ template <bool kPairs>
 __global__ void combine_kernel(const __half *__restrict__ rows, const int32_t *__restrict__ pairs_by_token,
                                const float *__restrict__ weights, __half *__restrict__ out,
                                int batch, int hidden, int top_k) {
+  // PDL: let the next kernel start its prologue; wait for the previous kernel's results
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int b = blockIdx.y;
   const int h2 = blockIdx.x * blockDim.x + threadIdx.x;   // pair of columns
   if (b >= batch || h2 * 2 >= hidden) return;
@@ -219,24 +231,38 @@ __global__ void combine_kernel(const __half *__restrict__ rows, const int32_t *_
       __halves2half2(__float2half_rn(a0), __float2half_rn(a1));
 }
 
+// Launch with the programmatic-stream-serialisation attribute (PDL).
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  count_launch();
+  return FB2_OK;
+}
+
 }  // namespace
 
 int launch_route_topk_softmax(const __half *logits, int32_t *ids, float *wts, int batch,
                               int num_experts, int top_k, int norm, cudaStream_t stream) {
   if (batch <= 0) return FB2_OK;
-  router_kernel<<<batch, 32, (size_t)num_experts * sizeof(float), stream>>>(
-      logits, ids, wts, batch, num_experts, top_k, norm);
-  FB2_LAUNCH_CHECK();
-  return FB2_OK;
+  return launch_pdl(router_kernel, dim3(batch), dim3(32), (size_t)num_experts * sizeof(float), stream, logits, ids,
+                    wts, batch, num_experts, top_k, norm);
 }
 
 int launch_build_pairs(const int32_t *expert_ids, int32_t *pairs_by_token,
                        int32_t *packed_token_idx, int32_t *expert_offsets, int pairs,
                        int num_experts, int top_k, cudaStream_t stream) {
-  build_pairs_kernel<<<num_experts, kSortThreads, 0, stream>>>(
-      expert_ids, pairs_by_token, packed_token_idx, expert_offsets, pairs, num_experts, top_k);
-  FB2_LAUNCH_CHECK();
-  return FB2_OK;
+  return launch_pdl(build_pairs_kernel, dim3(num_experts), dim3(kSortThreads), 0, stream, expert_ids, pairs_by_token,
+                    packed_token_idx, expert_offsets, pairs, num_experts, top_k);
 }
 
 int launch_align_block_size(const int32_t *expert_ids, int32_t *sorted_ids, int32_t *block_ids,
@@ -246,11 +272,8 @@ int launch_align_block_size(const int32_t *expert_ids, int32_t *sorted_ids, int3
     set_error("moe_align_block_size: num_experts %d > %d", num_experts, kMaxExperts);
     return FB2_ERR_UNSUPPORTED;
   }
-  align_block_size_kernel<<<num_experts, kSortThreads, 0, stream>>>(
-      expert_ids, sorted_ids, block_ids, total_post_pad, pairs, num_experts, block_size,
-      sorted_max, pair_ids);
-  FB2_LAUNCH_CHECK();
-  return FB2_OK;
+  return launch_pdl(align_block_size_kernel, dim3(num_experts), dim3(kSortThreads), 0, stream, expert_ids, sorted_ids,
+                    block_ids, total_post_pad, pairs, num_experts, block_size, sorted_max, pair_ids);
 }
 
 int launch_moe_combine(const __half *packed_down, const int32_t *pairs_by_token,
@@ -259,13 +282,10 @@ int launch_moe_combine(const __half *packed_down, const int32_t *pairs_by_token,
   if (batch <= 0) return FB2_OK;
   dim3 grid((hidden / 2 + 127) / 128, batch);
   if (pairs_by_token)
-    combine_kernel<true><<<grid, 128, 0, stream>>>(packed_down, pairs_by_token, weights, out, batch,
-                                                   hidden, top_k);
-  else
-    combine_kernel<false><<<grid, 128, 0, stream>>>(packed_down, nullptr, weights, out, batch,
-                                                    hidden, top_k);
-  FB2_LAUNCH_CHECK();
-  return FB2_OK;
+    return launch_pdl(combine_kernel<true>, grid, dim3(128), 0, stream, packed_down, pairs_by_token, weights, out,
+                      batch, hidden, top_k);
+  return launch_pdl(combine_kernel<false>, grid, dim3(128), 0, stream, packed_down, (const int32_t *)nullptr, weights,
+                    out, batch, hidden, top_k);
 }
 
 }  // namespace fb2
