@@ -250,6 +250,18 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+// ------------------------------------------------------------- cross-CTA signalling (gpu scope)
+// fire-and-forget release increment: orders this thread's (and, through a preceding CTA
+// barrier, the CTA's) earlier global writes before the counter update; no round trip
+__device__ __forceinline__ void red_release_add(int *addr, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int *addr) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------------------ misc
 __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint32_t orv) {
   uint32_t d;

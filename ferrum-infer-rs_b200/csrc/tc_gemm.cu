@@ -83,7 +83,7 @@ struct TcParams {
   RowMap rm;
   const __half *x;
   __half *y;
-  float *partials;        // [grid][2][NACC * NB * 128]
+  float *partials;        // [grid][NACC * NB * 128]: a CTA publishes at most one partial tile
   int32_t *counters;      // [row blocks * n_tiles], zero between launches
   int n_tiles;            // output tiles per row block (N/128, or I/128 with the SiLU epilogue)
   int groups;             // K / 128
@@ -246,7 +246,6 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   const uint32_t bars = smem_base + S * SC::kStride;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + S * SC::kStride + 512);
-  int *s_flag = reinterpret_cast<int *>(smem + S * SC::kStride + 516);
   const size_t tile_stride = (size_t)groups * kStageBytes;
 
   // ------------------------------------------------------------------ one-time setup
@@ -510,7 +509,35 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       const int col = tile * kTileN + nl;
       const float bias = (!kSilu && p.w.bias) ? p.w.bias[col] : 0.0f;
       const bool whole = (r_begin == 0 && r_end == upt);         // this CTA covered the whole tile
-      float *part = p.partials + ((size_t)cta * 2 + (sg.at_start ? 0 : 1)) * kPart;
+      // A tile cut by CTA range boundaries has contributors c_first .. c_last (consecutive CTAs).
+      // c_first -- whose piece of the tile is the LAST segment of its range -- owns the tile: it
+      // keeps its own accumulator in registers, waits until the others have published their fp32
+      // partials and sums them in contributor order (deterministic).  The others (for them the
+      // tile is the FIRST segment of their range) store a partial and bump the tile counter with a
+      // fire-and-forget release increment, so they never stall in mid-stream.
+      int c_first = cta, c_last = cta;
+      if (!whole) {
+        const long long tile_u0 = (long long)tau * upt;
+        c_first = cta_of_unit(tile_u0, T, G);
+        c_last = cta_of_unit(tile_u0 + upt - 1, T, G);
+      }
+      const bool owner = !whole && cta == c_first;
+      if (owner) {
+        if (threadIdx.x == 0) {
+          const int need = c_last - c_first;
+#ifdef FB2_WAIT_TIMEOUT
+          const long long t0 = clock64();
+#endif
+          while (ptx::ld_acquire(p.counters + tau) < need) {
+#ifdef FB2_WAIT_TIMEOUT
+            if (clock64() - t0 > 4000000000LL) { printf("fb2: tile counter wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
+#endif
+          }
+          p.counters[tau] = 0;                                   // self-reset for the next launch
+        }
+        ptx::named_bar_sync(1, kDequantWarps * 32);
+      }
+      float *part = p.partials + (size_t)cta * kPart;
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ch++) {
         float v[NACC][CH];
@@ -524,7 +551,23 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
             for (int j = 0; j < CH; j++) v[a][j] = 0.0f;
           }
         }
-        if (whole) {
+        const size_t row_off = (size_t)(h * HALF + ch * CH) * kTileN + nl;
+        if (owner) {
+          // contributors outermost, rows unrolled inside: CH * NACC independent L2 loads in flight
+          for (int c = c_first + 1; c <= c_last; c++) {
+            const float *src = p.partials + (size_t)c * kPart + row_off;
+            float t[NACC][CH];
+#pragma unroll
+            for (int a = 0; a < NACC; a++)
+#pragma unroll
+              for (int j = 0; j < CH; j++) t[a][j] = __ldcg(src + (size_t)(a * NB + j) * kTileN);
+#pragma unroll
+            for (int a = 0; a < NACC; a++)
+#pragma unroll
+              for (int j = 0; j < CH; j++) v[a][j] += t[a][j];
+          }
+        }
+        if (whole || owner) {
 #pragma unroll
           for (int j = 0; j < CH; j++) {
             int ar, cr;
@@ -536,69 +579,17 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
 #pragma unroll
           for (int a = 0; a < NACC; a++)
 #pragma unroll
-            for (int j = 0; j < CH; j++)
-              part[(size_t)(a * NB + h * HALF + ch * CH + j) * kTileN + nl] = v[a][j];
+            for (int j = 0; j < CH; j++) part[row_off + (size_t)(a * NB + j) * kTileN] = v[a][j];
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar(BAR_ACC_EMPTY));      // accumulators may be overwritten
-      if (!whole) {
-        // partial tile: fp32 partial stored above; last arriver reduces in contributor order
+      if (!whole && !owner) {
         FB2_STAMP(4);
-        ptx::named_bar_sync(1, kDequantWarps * 32);              // all partial stores issued (CTA scope)
-        const long long tile_u0 = (long long)tau * upt;
-        const int c_first = cta_of_unit(tile_u0, T, G), c_last = cta_of_unit(tile_u0 + upt - 1, T, G);
-        if (threadIdx.x == 0) {
-          __threadfence();                                       // cumulative: publishes the CTA's partials
-          const int contributors = c_last - c_first + 1;
-          const int old = atomicAdd(p.counters + tau, 1);
-          const int last = (old == contributors - 1);
-          if (last) {
-            p.counters[tau] = 0;                                 // self-reset for the next launch
-            __threadfence();                                     // acquire side: see the others' partials
-          }
-          *s_flag = last;
-        }
-        ptx::named_bar_sync(1, kDequantWarps * 32);
+        ptx::named_bar_sync(1, kDequantWarps * 32);              // every partial store of the CTA is issued
+        if (threadIdx.x == 0) ptx::red_release_add(p.counters + tau, 1);
         FB2_STAMP(5);
-        if (*s_flag) {
-          // Contributors outermost, rows unrolled inside: CH * NACC independent L2 loads are in
-          // flight per step (a row-outer loop would serialise one L2 round trip per addend).
-          const size_t first_off = ((size_t)c_first * 2 + (range_start(c_first, T, G) >= tile_u0 ? 0 : 1)) * kPart;
-#pragma unroll 1
-          for (int ch = 0; ch < NCH; ch++) {
-            float sum[NACC][CH];
-#pragma unroll
-            for (int a = 0; a < NACC; a++)
-#pragma unroll
-              for (int j = 0; j < CH; j++) sum[a][j] = 0.0f;
-            const size_t row_off = (size_t)(h * HALF + ch * CH) * kTileN + nl;
-            const float *src = p.partials + first_off + row_off;
-            for (int c = c_first; c <= c_last; c++) {
-              float t[NACC][CH];
-#pragma unroll
-              for (int a = 0; a < NACC; a++)
-#pragma unroll
-                for (int j = 0; j < CH; j++) t[a][j] = __ldcg(src + (size_t)(a * NB + j) * kTileN);
-#pragma unroll
-              for (int a = 0; a < NACC; a++)
-#pragma unroll
-                for (int j = 0; j < CH; j++) sum[a][j] += t[a][j];
-              // every contributor after the first starts inside the tile -> its slot 0
-              src = p.partials + ((size_t)(c + 1) * 2) * kPart + row_off;
-            }
-#pragma unroll
-            for (int j = 0; j < CH; j++) {
-              int ar, cr;
-              if (!rowmap_resolve(p.rm, tbl, NB, blk, h * HALF + ch * CH + j, ar, cr)) continue;
-              const float o = kSilu ? silu_mul(sum[0][j], sum[NACC - 1][j]) : sum[0][j] + bias;
-              p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
-            }
-          }
-        }
-        ptx::named_bar_sync(1, kDequantWarps * 32);              // s_flag may be rewritten next segment
-        FB2_STAMP(6);
       }
     }
 #ifdef FB2_TIMELINE
@@ -669,7 +660,7 @@ TcPlan make_plan(const WeightRef &w, const RowMap &rows, int epilogue, int sm_co
   long long g = units / 2;                       // >= 2 units per CTA: amortise setup / epilogue
   if (g < 1) g = 1;
   pl.grid = (int)(g < slots ? g : slots);
-  pl.partial_floats = (size_t)pl.grid * 2 * pl.nacc * pl.nb * kTileN;
+  pl.partial_floats = (size_t)pl.grid * pl.nacc * pl.nb * kTileN;
   pl.counters = (size_t)pl.row_blocks * pl.n_tiles;
   pl.smem = pl.nb == 16 ? smem_of<16>() : pl.nb == 32 ? smem_of<32>() : pl.nb == 64 ? smem_of<64>()
             : pl.nb == 128 ? smem_of<128>() : smem_of<256>();
