@@ -236,11 +236,16 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   const int G = (int)gridDim.x, cta = (int)blockIdx.x;
   const int groups = p.groups, n_tiles = p.n_tiles;
   const int upt = NACC * groups;                                 // units per output tile
-  // Routed mode reads the padded length the align kernel (an earlier kernel) produced.
-  if (p.rm.mode == ROWS_ROUTED) ptx::grid_dependency_wait();
-  const long long T = (long long)rowmap_num_blocks(p.rm, NB) * n_tiles * upt;
-  const long long u0 = range_start(cta, T, G), u1 = range_start(cta + 1, T, G);
-  if (u0 >= u1) return;                                          // CTA-uniform, before any barrier
+  // Routed mode learns its block count from the align kernel (an earlier kernel): its unit range
+  // is computed after the grid dependency, i.e. after the dependency-free part of the setup.
+  const bool routed = p.rm.mode == ROWS_ROUTED;
+  long long T = 0, u0 = 0, u1 = 0;
+  if (!routed) {
+    T = (long long)rowmap_num_blocks(p.rm, NB) * n_tiles * upt;
+    u0 = range_start(cta, T, G);
+    u1 = range_start(cta + 1, T, G);
+    if (u0 >= u1) return;                                        // CTA-uniform, before any barrier
+  }
 
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t bars = smem_base + S * SC::kStride;
@@ -278,6 +283,14 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(s_tmem));
   }
 
+  if (routed) {
+    ptx::grid_dependency_wait();
+    T = (long long)rowmap_num_blocks(p.rm, NB) * n_tiles * upt;
+    u0 = range_start(cta, T, G);
+    u1 = range_start(cta + 1, T, G);
+  }
+  const bool idle = u0 >= u1;                                    // routed launch with fewer units than CTAs
+
   const uint64_t pol = ptx::policy_evict_first();
   auto weight_src = [&](int blk, int tile, int phase, int g) {
       const int expert = rowmap_block_expert(p.rm, tbl, blk);
@@ -288,7 +301,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   // PDL prologue: weight stages depend on no earlier kernel's output -> up to S of them are
   // issued before the grid dependency (and before the rest of the CTA finished its setup).
   int pre = 0;
-  if (warp == kWarpTma) {
+  if (warp == kWarpTma && !idle) {
     {
       SegIter si;
       si.init(u0, u1, upt, n_tiles);
@@ -322,7 +335,9 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     tmem_base = *s_tmem;
   }
 
-  if (warp == kWarpTma) {
+  if (idle) {
+    // nothing to stream; fall through to the teardown (TMEM was allocated)
+  } else if (warp == kWarpTma) {
     // ================================================================== producer
     ptx::grid_dependency_wait();
     // rows of the current block: lane i holds row i (and i + 32 for NB == 64)
