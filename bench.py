@@ -31,6 +31,10 @@ LLAMA = {"hidden": 4096, "inter": 14336, "layers": 32,
          "linears": [("qkv_proj", 4096, 6144), ("o_proj", 4096, 4096),
                      ("gate_up_proj", 4096, 28672), ("down_proj", 14336, 4096)]}
 QWEN3 = {"hidden": 2048, "inter": 768, "experts": 128, "top_k": 8, "layers": 48}
+# Gemma3-27B (crates/ferrum-quantization/tests/gptq_parity_test.rs:584-660): desc_act checkpoint, GELU-tanh gate
+GEMMA3 = {"hidden": 5376, "inter": 21504, "q": 4096, "kv": 2048,
+          "linears": [("qkv_proj", 5376, 8192), ("o_proj", 4096, 5376), ("gate_up_proj", 5376, 43008),
+                      ("down_proj", 21504, 5376)]}
 DECODE_MS = [1, 2, 4, 8, 16, 32]
 GROUP = 128
 
@@ -330,6 +334,13 @@ def run_gpu(args):
                "d2h_bytes_per_step": sum(int(t.nbytes) for m in DECODE_MS for t in hy[m]) * world,
                "ms_per_step": round(e_ms, 3), "api": "GptqLinear.forward + all_reduce (per rank)"}
 
+    # ------------------------------------------- Gemma3-27B TP prefill (BASELINE.json configs[4])
+    tp_prefill = None
+    if not args.quick and not args.no_tp_prefill:
+        del lins
+        torch.cuda.empty_cache()
+        tp_prefill = run_tp_prefill(args, fb2, par, rank, world, local, pk)
+
     # ---------------------------------------------------------------------- MoE series
     moe = None
     if not args.quick and not args.no_moe:
@@ -368,7 +379,8 @@ def run_gpu(args):
                          "kernel": "tc_gemm_kernel (stream-K, tcgen05)", "avg_launch_us": round(avg_launch_us, 3),
                          "alg_bytes_per_launch": int(step_bytes / n_gemms)},
             "cpu_baseline": cpu, "series_decode": series, "per_shape_M1": per_shape, "prefill": prefill,
-            "moe_decode": moe, "build_s": round(build_s, 1), "host_cores": os.cpu_count(),
+            "moe_decode": moe, "tp_prefill_gemma3": tp_prefill, "build_s": round(build_s, 1),
+            "host_cores": os.cpu_count(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -376,6 +388,50 @@ def run_gpu(args):
         barrier(world)
         sys.stdout.flush()
         os._exit(0)
+
+
+def run_tp_prefill(args, fb2, par, rank, world, local, pk):
+    """Gemma3-27B GPTQ-Int4 dense linears, prefill M tokens, tensor parallel over `world` GPUs:
+    qkv (column) -> o (row + all-reduce) -> gate_up (column) -> GELU-tanh*up (local) -> down (row +
+    all-reduce).  Act-order on every layer; row-parallel shards are cut in g_idx-sorted order."""
+    import torch
+    dev = f"cuda:{local}"
+    M, layers = args.tp_prefill_m, args.tp_prefill_layers
+    wrng = np.random.default_rng(2727)
+    mods = []
+    for _ in range(layers):
+        row = {}
+        for (name, k, n) in GEMMA3["linears"]:
+            qw, sc, qz, gi = synth_gptq(wrng, k, n, act_order=not args.no_act_order)
+            row[name] = par.TensorParallelLinear(name, qw, sc, qz, gi, None, 4, GROUP, k, n, rank, world, device=local,
+                                                 qkv_segments=[GEMMA3["q"], GEMMA3["kv"], GEMMA3["kv"]])
+        mods.append(row)
+    fb2.pregrow_scratch(local, M)
+    H, I, Q = GEMMA3["hidden"], GEMMA3["inter"], GEMMA3["q"]
+    x = torch.randn(M, H, device=dev).clamp_(-1, 1).half()
+    qkv = torch.empty(M, mods[0]["qkv_proj"].n_local, device=dev, dtype=torch.float16)
+    attn = torch.empty(M, Q // world, device=dev, dtype=torch.float16)
+    h1 = torch.empty(M, H, device=dev, dtype=torch.float16)
+    gu = torch.empty(M, mods[0]["gate_up_proj"].n_local, device=dev, dtype=torch.float16)
+    act = torch.empty(M, I // world, device=dev, dtype=torch.float16)
+    h2 = torch.empty(M, H, device=dev, dtype=torch.float16)
+
+    def fn():
+        for m in mods:
+            m["qkv_proj"].forward(x, qkv, M)
+            attn.copy_(qkv[:, : Q // world])                   # stand-in for attention: the local q heads
+            m["o_proj"].forward(attn, h1, M)                   # + all-reduce
+            m["gate_up_proj"].forward(h1, gu, M)
+            fb2.moe.fused_gelu_tanh_mul_split(gu, act, M, I // world)
+            m["down_proj"].forward(act, h2, M)                 # + all-reduce
+    g = capture(fn)
+    t = time_graph(g, 3, 2, world) / 3                         # ms per pass over `layers` layers
+    flops = 2.0 * M * sum(k * n for (_, k, n) in GEMMA3["linears"]) * layers
+    tf = flops / (t * 1e-3) / 1e12
+    del g
+    return {"M": M, "layers": layers, "tflops_total": round(tf, 1), "tflops_per_gpu": round(tf / world, 1),
+            "frac_tensor_per_gpu": round(tf / world / pk["tflops_sustained"], 4), "ms_per_layer": round(t / layers, 3),
+            "parallelism": f"tp{world}", "all_reduce": "nccl (torch.distributed), fp16 [M, hidden], 2 per layer"}
 
 
 def run_moe(args, fb2, par, rank, world, local, pk):
@@ -513,6 +569,9 @@ def main():
     ap.add_argument("--moe-batches", type=int, nargs="+", default=[1, 2, 4, 8, 16, 32])
     ap.add_argument("--no-act-order", action="store_true")
     ap.add_argument("--no-moe", action="store_true")
+    ap.add_argument("--no-tp-prefill", action="store_true")
+    ap.add_argument("--tp-prefill-m", type=int, default=4096)
+    ap.add_argument("--tp-prefill-layers", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="headline only (used under ncu)")
     args = ap.parse_args()
