@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfb2_w4a16.so")
+# FB2_LIB selects another build of the same library (A/B measurements, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("FB2_LIB") or os.path.join(_HERE, "libfb2_w4a16.so")
 
 FB2_OK = 0
 ERR_NAMES = {-1: "FB2_ERR_SHAPE", -2: "FB2_ERR_UNSUPPORTED", -3: "FB2_ERR_CUDA",

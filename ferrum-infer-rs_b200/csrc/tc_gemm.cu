@@ -67,6 +67,15 @@ template <int NB>
 struct StageCfg {
   static constexpr bool kWide = NB >= 128;
   static constexpr int kCtasPerSm = kWide ? 1 : 2;
+  // Registers are allocated per warp in groups of four warps: a 10-warp CTA occupies the register
+  // space of 12, so two CTAs are co-resident only below 65536 / (2 * 12 * 32) = 85 registers per
+  // thread.  Declaring 384 threads to the compiler makes it hold that budget (80); the launch still
+  // uses kThreads.  (At 96 registers the occupancy query answers ONE CTA per SM.)
+#ifdef FB2_REGS96
+  static constexpr int kBoundThreads = kThreads;
+#else
+  static constexpr int kBoundThreads = kWide ? kThreads : 384;
+#endif
   static constexpr int kTmemCols = kWide ? 512 : 256;
   static constexpr int kTmemABase = kWide ? 256 : 128;
   static constexpr int kASlots = kWide ? 4 : 2;                               // slots of one 128-k group (64 columns)
@@ -214,8 +223,37 @@ struct RingPos {
   }
 };
 
-template <int NB, bool kSilu>
-__device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *tbl, const CUtensorMap *xmap) {
+#ifdef FB2_TRACE
+__device__ long long *g_trace = nullptr;      // pinned host memory: [cta][32] progress markers (debug builds only)
+#if FB2_TRACE >= 2   // per-unit progress markers (slow: every marker is a posted write to host memory)
+#define FB2_MARK(v) do { if (g_trace && (threadIdx.x & 31) == 0) { \
+    *((volatile long long *)g_trace + (size_t)blockIdx.x * 32 + (threadIdx.x >> 5)) = (long long)(v); } } while (0)
+#else
+#define FB2_MARK(v) do { } while (0)
+#endif
+#define FB2_MARK2(slot, v) do { if (g_trace && (threadIdx.x & 31) == 0) { \
+    *((volatile long long *)g_trace + (size_t)blockIdx.x * 32 + 16 + (slot)) = (long long)(v); } } while (0)
+__device__ __forceinline__ long long fb2_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define FB2_TSTAMP(slot) do { if (g_trace && threadIdx.x == 0) { \
+    *((volatile long long *)g_trace + (size_t)blockIdx.x * 32 + 16 + (slot)) = fb2_gtime(); } } while (0)
+// timeline of one GEMM launch: [8 launches][296 CTAs][32] after the fused-kernel area
+#define FB2_TL(slot) do { if (g_trace && threadIdx.x == 0) { \
+    *((volatile long long *)g_trace + (size_t)(296 + (((p.x_tma >> 16) & 7) * 296 + blockIdx.x)) * 32 + (slot)) = fb2_gtime(); } } while (0)
+#define FB2_TLV(slot, v) do { if (g_trace && threadIdx.x == 0) { \
+    *((volatile long long *)g_trace + (size_t)(296 + (((p.x_tma >> 16) & 7) * 296 + blockIdx.x)) * 32 + (slot)) = (long long)(v); } } while (0)
+#else
+#define FB2_MARK(v) do { } while (0)
+#define FB2_MARK2(slot, v) do { } while (0)
+#define FB2_TSTAMP(slot) do { } while (0)
+#define FB2_TL(slot) do { } while (0)
+#define FB2_TLV(slot, v) do { } while (0)
+#endif
+
+template <int NB, bool kSilu, bool kReentrant = false>
+__device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *tbl, const CUtensorMap *xmap,
+                                        uint32_t ext_tmem = 0xFFFFFFFFu) {
+  // ext_tmem != ~0: tensor memory was allocated by the caller (the fused MoE kernel runs this body
+  // twice; a CTA may not allocate again after tcgen05.relinquish_alloc_permit)
   extern __shared__ __align__(1024) uint8_t smem[];
   using SC = StageCfg<NB>;
   constexpr int kTmemCols = SC::kTmemCols, kTmemABase = SC::kTmemABase, kASlots = SC::kASlots;
@@ -233,7 +271,9 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
 #define FB2_STAMP(i) do { } while (0)
 #endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  FB2_TL(0);
+  int G = (int)gridDim.x;                                        // CTAs that take part (see below)
+  const int cta = (int)blockIdx.x;
   const int groups = p.groups, n_tiles = p.n_tiles;
   const int upt = NACC * groups;                                 // units per output tile
   // Routed mode learns its block count from the align kernel (an earlier kernel): its unit range
@@ -260,7 +300,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     if (lane == 0) {
       for (int i = 0; i < S; i++) {
         // one arrive.expect_tx by the producer (+ 32 cp.async arrivals when rows are gathered)
-        ptx::mbar_init(bar(BAR_FULL + i), p.x_tma ? 1 : 1 + 32);
+        ptx::mbar_init(bar(BAR_FULL + i), (p.x_tma & 1) ? 1 : 1 + 32);
         ptx::mbar_init(bar(BAR_EMPTY + i), kDequantWarps + 1);    // 8 warps + the MMA commit
       }
       ptx::mbar_fence_init();
@@ -280,16 +320,25 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       ptx::mbar_fence_init();
     }
     __syncwarp();
-    ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(s_tmem));
+    if (ext_tmem == 0xFFFFFFFFu) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(s_tmem));
   }
 
   if (routed) {
     ptx::grid_dependency_wait();
     T = (long long)rowmap_num_blocks(p.rm, NB) * n_tiles * upt;
-    u0 = range_start(cta, T, G);
-    u1 = range_start(cta + 1, T, G);
+    // The grid was sized for the worst-case block count; with fewer units only the first
+    // max(1, T/2) CTAs take part, so that every participating CTA owns a non-empty range and the
+    // contributors of a tile are exactly the consecutive CTAs c_first .. c_last.
+    const long long g_eff = T / 2 > 1 ? T / 2 : 1;
+    if (g_eff < G) G = (int)g_eff;
+    if (cta < G) {
+      u0 = range_start(cta, T, G);
+      u1 = range_start(cta + 1, T, G);
+    }
   }
   const bool idle = u0 >= u1;                                    // routed launch with fewer units than CTAs
+  FB2_MARK(1);
+  if (warp == 0) { FB2_MARK2(0, T); FB2_MARK2(1, G); FB2_MARK2(2, u0); FB2_MARK2(3, u1); }
 
   const uint64_t pol = ptx::policy_evict_first();
   auto weight_src = [&](int blk, int tile, int phase, int g) {
@@ -332,8 +381,11 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     ptx::tc_fence_before();
     ptx::named_bar_sync(2, kThreads);
     ptx::tc_fence_after();
-    tmem_base = *s_tmem;
+    tmem_base = ext_tmem == 0xFFFFFFFFu ? *s_tmem : ext_tmem;
   }
+  FB2_MARK(2);
+  FB2_TL(1);
+  FB2_TLV(8, u1 - u0);
 
   if (idle) {
     // nothing to stream; fall through to the teardown (TMEM was allocated)
@@ -342,14 +394,14 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     ptx::grid_dependency_wait();
     // rows of the current block: lane i holds row i (and i + 32 for NB == 64)
     int cur_blk = -1, nchunks = 0, arow0 = -1, arow1 = -1, row0 = 0;
-    if (p.x_tma && lane == 0) ptx::prefetch_tensormap(xmap);
+    if ((p.x_tma & 1) && lane == 0) ptx::prefetch_tensormap(xmap);
     RingPos rp{0, 0};
     int it = 0;
     SegIter si;
     si.init(u0, u1, upt, n_tiles);
     Seg sg;
     while (si.next(sg, upt, n_tiles)) {
-      if (sg.blk != cur_blk && p.x_tma) {
+      if (sg.blk != cur_blk && (p.x_tma & 1)) {
         cur_blk = sg.blk;
         int ar, cr;
         rowmap_resolve(p.rm, tbl, NB, sg.blk, 0, ar, cr);        // dense / dispatch: rows are contiguous
@@ -376,19 +428,20 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         for (int g = g0; g < g1; g++, it++, wsrc += kStageBytes, xg += kGroup, rp.advance(S)) {
           const uint32_t stage_addr = smem_base + rp.st * SC::kStride;
           const uint32_t full = bar(BAR_FULL + rp.st);
+          FB2_MARK(100 + it);
           if (it >= pre) ptx::mbar_wait(bar(BAR_EMPTY + rp.st), rp.par ^ 1u);
           if (ptx::elect_one()) {
-            const uint32_t tx = (it >= pre ? (uint32_t)kStageBytes : 0u) + (p.x_tma ? (uint32_t)SC::kXBytes : 0u);
+            const uint32_t tx = (it >= pre ? (uint32_t)kStageBytes : 0u) + ((p.x_tma & 1) ? (uint32_t)SC::kXBytes : 0u);
             ptx::mbar_arrive_expect_tx(full, tx);
             if (it >= pre) ptx::bulk_g2s_hint(stage_addr + SC::kXBytes, wsrc, kStageBytes, full, pol);
-            if (p.x_tma) {
+            if (p.x_tma & 1) {
               // [NB rows x 64 k] boxes, hardware 128B swizzle; rows past the tensor end read as zero
               ptx::tma_load_2d(stage_addr, xmap, g * kGroup, row0, full);
               ptx::tma_load_2d(stage_addr + NB * 128, xmap, g * kGroup + 64, row0, full);
             }
           }
           __syncwarp();
-          if (!p.x_tma) {
+          if (!(p.x_tma & 1)) {
             // gathered activation slice: rows [0, nvalid) x 128 k, 16 chunks of 16 B per row
             for (int ch0 = 0; ch0 < nchunks; ch0 += 32) {         // warp-uniform trip count
               const int ch = ch0 + lane;
@@ -406,6 +459,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       }
     }
     __syncwarp();
+    FB2_MARK(199);
   } else if (warp == kWarpMma) {
     // ==================================================================== MMA issuer
     // Warp-uniform branch + elect.sync predicate: ptxas emits straight-line UTCHMMA with
@@ -426,6 +480,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         const uint32_t d_tmem = tmem_base + a * NB;
 #pragma unroll 1
         for (int g = g0; g < g1; g++, rp.advance(S), ap.advance(kASlots)) {
+          FB2_MARK(200 + g);
           ptx::mbar_wait(bar(BAR_FULL + rp.st), rp.par);          // activations (and weights) landed
           ptx::fence_proxy_async_smem();                          // cp.async data -> async proxy
           const uint64_t b_desc0 = b_desc_ring + (uint64_t)((rp.st * SC::kStride) >> 4);
@@ -452,6 +507,23 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       __syncwarp();
       seg++;
     }
+    // Drain: tcgen05.commit arrivals are asynchronous and nobody waits for the last use of each
+    // stage / A slot.  Wait for them here so that the barriers can be invalidated (and re-initialised
+    // by a second pass of this body in the fused MoE kernel) without racing a late arrival.
+    FB2_MARK(290);
+    if constexpr (kReentrant) {
+      const int n_units = (int)(u1 - u0);
+      for (int st = 0; st < S && st < n_units; st++) {
+        const int uses = (n_units - st + S - 1) / S;
+        ptx::mbar_wait(bar(BAR_EMPTY + st), (uint32_t)((uses - 1) & 1));
+      }
+      for (int a = 0; a < kASlots && a < n_units; a++) {
+        const int uses = (n_units - a + kASlots - 1) / kASlots;
+        ptx::mbar_wait(bar(BAR_EMPTY_A + a * 2 + 0), (uint32_t)((uses - 1) & 1));
+        ptx::mbar_wait(bar(BAR_EMPTY_A + a * 2 + 1), (uint32_t)((uses - 1) & 1));
+      }
+    }
+    FB2_MARK(299);
   } else {
     // ======================================================== dequant + epilogue warps
     const int q = warp & 3;               // TMEM lane quarter this warp may access
@@ -466,6 +538,8 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     int seg = 0;
     FB2_STAMP(0);
     ptx::grid_dependency_wait();          // before the first global write / scratch access
+    FB2_TL(2);
+    bool tl_first = true;
     SegIter si;
     si.init(u0, u1, upt, n_tiles);
     Seg sg;
@@ -473,7 +547,10 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
 #pragma unroll 1
       for (int n = sg.r1 - sg.r0; n > 0; n--, rp.advance(S), ap.advance(kASlots)) {
         const uint32_t stage_addr = smem_base + rp.st * SC::kStride;
+        FB2_MARK(300 + n);
         ptx::mbar_wait(bar(BAR_FULL + rp.st), rp.par);
+        FB2_MARK(350 + n);
+        if (tl_first) { FB2_TL(3); tl_first = false; }
         const uint32_t sz = ptx::lds32(stage_addr + sz_off);
         const uint4 w0 = ptx::lds128(stage_addr + w_off);
         const uint4 w1 = ptx::lds128(stage_addr + w_off + 2048u);
@@ -512,7 +589,11 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       const int r_begin = sg.r0, r_end = sg.r1;                  // [r_begin, r_end) of [0, upt)
       const int blk = sg.blk, tile = sg.tile, tau = sg.blk * n_tiles + sg.tile;
       FB2_STAMP(2);
+      FB2_TL(4);
+      FB2_MARK(400 + seg);
       ptx::mbar_wait(bar(BAR_ACC), seg & 1);
+      FB2_MARK(410 + seg);
+      FB2_TL(5);
       FB2_STAMP(3);
       seg++;
       ptx::tc_fence_after();
@@ -538,6 +619,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       }
       const bool owner = !whole && cta == c_first;
       if (owner) {
+        FB2_MARK(420 + seg);
         if (threadIdx.x == 0) {
           const int need = c_last - c_first;
 #ifdef FB2_WAIT_TIMEOUT
@@ -550,6 +632,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
           }
           p.counters[tau] = 0;                                   // self-reset for the next launch
         }
+        __syncwarp();                                            // reconverge before .sync.aligned tcgen05.ld
         ptx::named_bar_sync(1, kDequantWarps * 32);
       }
       float *part = p.partials + (size_t)cta * kPart;
@@ -600,10 +683,12 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar(BAR_ACC_EMPTY));      // accumulators may be overwritten
+      FB2_TL(6);
       if (!whole && !owner) {
         FB2_STAMP(4);
         ptx::named_bar_sync(1, kDequantWarps * 32);              // every partial store of the CTA is issued
         if (threadIdx.x == 0) ptx::red_release_add(p.counters + tau, 1);
+        __syncwarp();
         FB2_STAMP(5);
       }
     }
@@ -615,23 +700,230 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   }
 
   // -------------------------------------------------------------------------- teardown
+  FB2_MARK(900);
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == kWarpMma) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  FB2_MARK(901);
+  if (warp == kWarpMma) {
+    if (ext_tmem == 0xFFFFFFFFu) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+    // the fused MoE kernel runs this body twice in one launch: leave no live mbarrier objects
+    if (kReentrant && lane == 0) {
+      for (int i = 0; i < 2 * kASlots; i++) { ptx::mbar_inval(bar(BAR_FULL_A + i)); ptx::mbar_inval(bar(BAR_EMPTY_A + i)); }
+      ptx::mbar_inval(bar(BAR_ACC));
+      ptx::mbar_inval(bar(BAR_ACC_EMPTY));
+    }
+  } else if (kReentrant && warp == kWarpTma && lane == 0) {
+    for (int i = 0; i < S; i++) { ptx::mbar_inval(bar(BAR_FULL + i)); ptx::mbar_inval(bar(BAR_EMPTY + i)); }
+  }
+  if constexpr (kReentrant) __syncthreads();
+  FB2_MARK(999);
+  FB2_TL(7);
 }
 
 template <int NB, bool kSilu>
-__global__ void __launch_bounds__(kThreads, StageCfg<NB>::kCtasPerSm)
+__global__ void __launch_bounds__(StageCfg<NB>::kBoundThreads, StageCfg<NB>::kCtasPerSm)
 tc_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
   ptx::launch_dependents();
   tc_body<NB, kSilu>(p, nullptr, &xmap);
 }
 template <int NB>
-__global__ void __launch_bounds__(kThreads, StageCfg<NB>::kCtasPerSm)
+__global__ void __launch_bounds__(StageCfg<NB>::kBoundThreads, StageCfg<NB>::kCtasPerSm)
 tc_gemm_dispatch_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap,
                         const __grid_constant__ DispatchTable tbl) {
   ptx::launch_dependents();
   tc_body<NB, false>(p, &tbl, &xmap);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused MoE FFN for decode-sized batches: ONE persistent launch does
+//   route + align (CTA 0)  | grid barrier |  gate||up grouped GEMM + SiLU*up  | grid barrier |
+//   down grouped GEMM      | grid barrier |  weighted combine
+// i.e. steps 1-6 of moe_forward_bucketed (crates/ferrum-models/src/moe/dispatch.rs:1558-2192), which
+// the reference runs as 8-11 launches.  At batch 1 a layer touches 19.6 MB (3 us of HBM time); five
+// dependent launches cost ten times that, so the launch gaps are what this kernel removes.
+// All CTAs are co-resident (grid = 2 per SM), which is what makes the grid barriers legal.
+struct MoeFusedArgs {
+  const __half *logits;   // [batch, E]
+  int32_t *ids;           // [batch * K]
+  float *wts;             // [batch * K]
+  int32_t *sorted;        // [cap]
+  int32_t *block_ids;     // [cap / block + 1]
+  int32_t *total;         // [1]
+  const __half *down_out; // [pairs, H]   (phase-2 output)
+  __half *out;            // [batch, H]
+  int32_t *sync;          // [2] arrive counter, exit counter (zero between launches)
+  int batch, num_experts, top_k, norm, hidden, block, cap;
+};
+
+__device__ __forceinline__ void grid_barrier(int32_t *arrive, int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(arrive, 1);
+    const long long t0 = clock64();
+    while (ptx::ld_acquire(arrive) < target) {
+      if (clock64() - t0 > 2000000000LL) {                     // ~1 s: a CTA that never became resident
+        printf("fb2: grid barrier timed out (cta %d, target %d)\n", blockIdx.x, target);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  // thread 0 left the warp for the spin loop: bar.sync does not reconverge it, and the tcgen05
+  // .sync.aligned instructions that follow need the whole warp executing together
+  __syncwarp();
+  __syncthreads();
+}
+
+// route (router.rs:113-195 semantics, as router_kernel) + align with pair ids, by ONE CTA
+__device__ __forceinline__ void route_align_cta(const MoeFusedArgs &m, float *scratch /* dynamic smem */) {
+  // carved from the (still unused) dynamic shared memory: [warps][E] floats, then three int arrays
+  int *s_ids = reinterpret_cast<int *>(scratch + (size_t)(blockDim.x >> 5) * m.num_experts);
+  int *s_cnt = s_ids + 1024;
+  int *s_off = s_cnt + 1024;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5, nthr = blockDim.x;
+  const int E = m.num_experts, K = m.top_k, pairs = m.batch * K;
+  for (int i = threadIdx.x; i < E; i += nthr) s_cnt[i] = 0;
+  float *probs = scratch + (size_t)warp * E;
+  for (int row = warp; row < m.batch; row += nwarps) {
+    float tmax = -INFINITY;
+    for (int i = lane; i < E; i += 32) {
+      float v = __half2float(m.logits[(size_t)row * E + i]);
+      probs[i] = v;
+      tmax = v > tmax ? v : tmax;
+    }
+    for (int o = 16; o; o >>= 1) {
+      float t = __shfl_xor_sync(0xffffffffu, tmax, o);
+      tmax = t > tmax ? t : tmax;
+    }
+    __syncwarp();
+    for (int i = lane; i < E; i += 32) probs[i] = expf(probs[i] - tmax);
+    __syncwarp();
+    float sum = 0.f;
+    if (lane == 0)
+      for (int i = 0; i < E; i++) sum += probs[i];               // left to right, as router.rs:150-155
+    sum = __shfl_sync(0xffffffffu, sum, 0);
+    const float inv = 1.0f / sum;
+    for (int i = lane; i < E; i += 32) probs[i] *= inv;
+    __syncwarp();
+    float sel_sum = 0.f;
+    for (int k = 0; k < K; k++) {
+      float best = -INFINITY;
+      int best_i = 0x7fffffff;
+      for (int i = lane; i < E; i += 32) {
+        float v = probs[i];
+        if (v > best) { best = v; best_i = i; }
+      }
+      for (int o = 16; o; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+      }
+      if (best_i == 0x7fffffff) best_i = 0;
+      if (lane == 0) {
+        m.ids[(size_t)row * K + k] = best_i;
+        m.wts[(size_t)row * K + k] = best;
+        s_ids[row * K + k] = best_i;
+        probs[best_i] = -INFINITY;
+      }
+      sel_sum += best;
+      __syncwarp();
+    }
+    if (m.norm) {
+      for (int k = lane; k < K; k += 32) {
+        if (sel_sum > 0.f) m.wts[(size_t)row * K + k] *= (1.0f / sel_sum);
+        else m.wts[(size_t)row * K + k] = 1.0f / (float)K;
+      }
+    }
+  }
+  __syncthreads();
+  for (int pidx = threadIdx.x; pidx < pairs; pidx += nthr) atomicAdd(&s_cnt[s_ids[pidx]], 1);    // counts only
+  __syncthreads();
+  if (warp == 0) {
+    // padded offsets: warp-level scan over experts, 32 at a time
+    int carry = 0;
+    for (int e0 = 0; e0 < E; e0 += 32) {
+      const int e = e0 + lane;
+      const int padded = e < E ? ((s_cnt[e] + m.block - 1) / m.block) * m.block : 0;
+      int incl = padded;
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (e < E) s_off[e] = carry + incl - padded;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) { s_off[E] = carry; m.total[0] = carry; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < m.cap; i += nthr) m.sorted[i] = pairs;                             // sentinel
+  __syncthreads();
+  for (int pidx = threadIdx.x; pidx < pairs; pidx += nthr) {
+    const int e = s_ids[pidx];
+    int rank = 0;
+    for (int q = 0; q < pidx; q++) rank += (s_ids[q] == e);       // ascending pair order == the host plan
+    const int slot = s_off[e] + rank;
+    if (slot < m.cap) m.sorted[slot] = pidx;
+  }
+  for (int e = threadIdx.x; e < E; e += nthr)
+    for (int b = s_off[e] / m.block; b < s_off[e + 1] / m.block; b++) m.block_ids[b] = e;
+}
+
+template <int NB, bool kSilu>
+__device__ __noinline__ void tc_body_outlined(const TcParams &p, uint32_t tmem) {
+  tc_body<NB, kSilu, true>(p, nullptr, nullptr, tmem);
+}
+
+__global__ void __launch_bounds__(StageCfg<16>::kBoundThreads, 2)
+moe_ffn_fused_kernel(const TcParams p1, const TcParams p2, const MoeFusedArgs m) {
+  extern __shared__ __align__(1024) uint8_t smem_fused[];
+  ptx::launch_dependents();
+  ptx::grid_dependency_wait();
+  const int G = (int)gridDim.x;
+  FB2_TSTAMP(4);
+  // no static shared memory in this kernel: the dynamic region must start at offset 0 so that the
+  // 1024-byte alignment the UMMA swizzle atoms need holds (tc_body carves it from the same base)
+  uint32_t *s_tmem_fused =
+      reinterpret_cast<uint32_t *>(smem_fused + StageCfg<16>::kStages * StageCfg<16>::kStride + 520);
+  const int warp = threadIdx.x >> 5;
+  if (warp == kWarpMma) ptx::tmem_alloc<256>(ptx::smem_u32(s_tmem_fused));      // once for both GEMM phases
+  if (blockIdx.x == 0) route_align_cta(m, reinterpret_cast<float *>(smem_fused));
+  FB2_TSTAMP(5);
+  ptx::tc_fence_before();
+  grid_barrier(m.sync, G);
+  ptx::tc_fence_after();
+  FB2_TSTAMP(6);
+  const uint32_t tmem = *s_tmem_fused;
+  tc_body_outlined<16, true>(p1, tmem);    // gate||up grouped GEMM, gather + SiLU*up fused
+  FB2_TSTAMP(7);
+  grid_barrier(m.sync, 2 * G);
+  FB2_TSTAMP(8);
+  tc_body_outlined<16, false>(p2, tmem);   // down grouped GEMM
+  FB2_TSTAMP(9);
+  grid_barrier(m.sync, 3 * G);
+  FB2_TSTAMP(10);
+  if (warp == kWarpMma) ptx::tmem_dealloc<256>(tmem);
+  // combine: out[b, h] = sum_k w[b, k] * down[b * K + k, h]  (capabilities.rs:565-600; overwrites out)
+  const int H2 = m.hidden / 2;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < m.batch * H2; idx += G * blockDim.x) {
+    const int b = idx / H2, h2 = idx - b * H2;
+    float a0 = 0.f, a1 = 0.f;
+    for (int k = 0; k < m.top_k; k++) {
+      const float w = m.wts[b * m.top_k + k];
+      const __half2 v = *reinterpret_cast<const __half2 *>(m.down_out + (size_t)(b * m.top_k + k) * m.hidden + h2 * 2);
+      a0 += w * __low2float(v);
+      a1 += w * __high2float(v);
+    }
+    *reinterpret_cast<__half2 *>(m.out + (size_t)b * m.hidden + h2 * 2) =
+        __halves2half2(__float2half_rn(a0), __float2half_rn(a1));
+  }
+  // last CTA out resets the barrier words for the next launch
+  FB2_TSTAMP(11);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(m.sync + 1, 1);
+    if (old == G - 1) { m.sync[0] = 0; m.sync[1] = 0; }
+  }
 }
 
 // ------------------------------------------------------------------------ host planning
@@ -825,6 +1117,20 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
     return FB2_ERR_ARG;
   }
 
+#ifdef FB2_TRACE
+  {
+    static int seq = 0;
+    static bool init = false;
+    if (!init) {
+      init = true;
+      if (const char *tb = getenv("FB2_DEBUG_BUF")) {
+        long long *hp = (long long *)strtoull(tb, nullptr, 10);
+        cudaMemcpyToSymbol(g_trace, &hp, sizeof(hp));
+      }
+    }
+    p.x_tma |= (seq++ & 7) << 16;
+  }
+#endif
   int rc;
   if (tbl) {
     rc = nb == 16 ? launch_dispatch<16>(pl, stream, p, xmap, *tbl)
@@ -839,6 +1145,110 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
          : nb == 128 ? launch_plain<128, false>(pl, stream, p, xmap) : launch_plain<256, false>(pl, stream, p, xmap);
   }
   if (rc) return rc;
+  count_launch();
+  return FB2_OK;
+}
+
+bool moe_fused_supported(const WeightRef &gu, const WeightRef &dn, size_t batch, size_t top_k) {
+  return tc_supported(gu) && tc_supported(dn) && gu.n % 2 == 0 && (gu.n / 2) % kTileN == 0 && batch >= 1 &&
+         batch <= 32 && batch * top_k <= 1024 && gu.num_experts <= 1024 && gu.perm == nullptr && dn.perm == nullptr;
+}
+
+static int fused_grid(int sm_count) {
+  // One CTA per SM: the occupancy query is conservative for kernels that allocate tensor memory (it
+  // answers 1 although two such CTAs do become co-resident -- scripts/ubench/occ_tmem.cu), and the
+  // in-kernel grid barriers must never wait for a CTA that is not resident.
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    cudaFuncSetAttribute(moe_ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageCfg<16>::kSmemBytes);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, moe_ffn_fused_kernel, kThreads, StageCfg<16>::kSmemBytes) != cudaSuccess)
+      n = 0;
+    per_sm = n > 2 ? 2 : n;
+    if (const char *e = getenv("FB2_DEBUG_FUSED_PER_SM")) per_sm = atoi(e);   // co-residency experiment
+  }
+  return per_sm * (sm_count > 0 ? sm_count : 148);
+}
+
+void moe_fused_requirements(const WeightRef &gu, const WeightRef &dn, size_t batch, size_t top_k, int sm_count,
+                            size_t *partial_bytes, size_t *counters) {
+  const int grid = fused_grid(sm_count);
+  const size_t pairs = batch * top_k;
+  const size_t nonempty = pairs < (size_t)gu.num_experts ? pairs : (size_t)gu.num_experts;
+  const size_t blocks = (pairs + nonempty * 15) / 16;
+  *partial_bytes = (size_t)grid * 2 * 16 * kTileN * sizeof(float);
+  const size_t t1 = blocks * (size_t)(gu.n / 2 / kTileN), t2 = blocks * (size_t)(dn.n / kTileN);
+  *counters = (t1 > t2 ? t1 : t2) + 2;               // + the two grid-barrier words
+}
+
+int launch_moe_ffn_fused(const WeightRef &gu, const WeightRef &dn, const __half *x, const __half *logits,
+                         __half *out, int32_t *ids, float *wts, int32_t *sorted, int32_t *block_ids,
+                         int32_t *total, __half *act, __half *down_out, size_t batch, size_t top_k, int norm,
+                         size_t cap, const TcScratch &scratch, int sm_count, cudaStream_t stream) {
+  const int grid = fused_grid(sm_count);
+  if (grid < 2) {
+    set_error("fused MoE kernel cannot be made resident");
+    return FB2_ERR_CUDA;
+  }
+  size_t pb, nc;
+  moe_fused_requirements(gu, dn, batch, top_k, sm_count, &pb, &nc);
+  if (pb > scratch.partial_bytes || nc > scratch.num_counters) {
+    set_error("split-K scratch too small for the fused MoE kernel: call fb2_pregrow_scratch");
+    return FB2_ERR_ARG;
+  }
+  const size_t pairs = batch * top_k;
+  const size_t nonempty = pairs < (size_t)gu.num_experts ? pairs : (size_t)gu.num_experts;
+  const int bound = (int)((pairs + nonempty * 15) / 16);
+  auto mk = [&](const WeightRef &w, const __half *xin, __half *yout, int tk, int epilogue) {
+    TcParams p{};
+    p.w = w;
+    p.rm.mode = ROWS_ROUTED;
+    p.rm.sorted_ids = sorted;
+    p.rm.block_experts = block_ids;
+    p.rm.num_post_padded = total;
+    p.rm.block = 16;
+    p.rm.top_k = tk;
+    p.rm.num_valid = (int)pairs;
+    p.rm.max_blocks = bound;
+    p.x = xin;
+    p.y = yout;
+    p.partials = scratch.partials;
+    p.counters = scratch.counters;
+    p.n_tiles = (epilogue ? w.n / 2 : w.n) / kTileN;
+    p.groups = w.k / kGroup;
+    p.tiles_per_expert = w.ld / kTileN;
+    p.ld_out = epilogue ? w.n / 2 : w.n;
+    p.x_tma = 0;
+    return p;
+  };
+  TcParams p1 = mk(gu, x, act, (int)top_k, 1);
+  TcParams p2 = mk(dn, act, down_out, 1, 0);
+#ifdef FB2_TRACE
+  if (const char *tb = getenv("FB2_DEBUG_BUF")) {
+    long long *hp = (long long *)strtoull(tb, nullptr, 10);
+    cudaMemcpyToSymbol(g_trace, &hp, sizeof(hp));
+    fprintf(stderr, "fb2 trace: fused grid %d (sm_count %d)\n", grid, sm_count);
+  }
+#endif
+  MoeFusedArgs m{};
+  m.logits = logits; m.ids = ids; m.wts = wts; m.sorted = sorted; m.block_ids = block_ids; m.total = total;
+  m.down_out = down_out; m.out = out;
+  m.sync = scratch.counters + (nc - 2);
+  m.batch = (int)batch; m.num_experts = gu.num_experts; m.top_k = (int)top_k; m.norm = norm;
+  m.hidden = dn.n; m.block = 16; m.cap = (int)cap;
+  FB2_CUDA_TRY(cudaFuncSetAttribute(moe_ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)StageCfg<16>::kSmemBytes));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = StageCfg<16>::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, moe_ffn_fused_kernel, p1, p2, m));
   count_launch();
   return FB2_OK;
 }
