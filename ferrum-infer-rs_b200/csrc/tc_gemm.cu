@@ -263,13 +263,6 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   static_assert(S >= 3, "smem ring too shallow");
   static_assert(NACC * NB <= kTmemABase, "accumulators overlap the A ring");
 
-#ifdef FB2_TIMELINE
-  const long long t_entry = clock64();
-  long long tl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define FB2_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) tl[i] = clock64() - t_entry; } while (0)
-#else
-#define FB2_STAMP(i) do { } while (0)
-#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FB2_TL(0);
   int G = (int)gridDim.x;                                        // CTAs that take part (see below)
@@ -386,15 +379,19 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   FB2_MARK(2);
   FB2_TL(1);
   FB2_TLV(8, u1 - u0);
+#ifdef FB2_TRACE
+  { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); FB2_TLV(10, smid); }
+#endif
 
   if (idle) {
     // nothing to stream; fall through to the teardown (TMEM was allocated)
   } else if (warp == kWarpTma) {
     // ================================================================== producer
+    // the descriptor is a kernel parameter: fetch it before the grid dependency resolves
+    if ((p.x_tma & 1) && lane == 0) ptx::prefetch_tensormap(xmap);
     ptx::grid_dependency_wait();
     // rows of the current block: lane i holds row i (and i + 32 for NB == 64)
     int cur_blk = -1, nchunks = 0, arow0 = -1, arow1 = -1, row0 = 0;
-    if ((p.x_tma & 1) && lane == 0) ptx::prefetch_tensormap(xmap);
     RingPos rp{0, 0};
     int it = 0;
     SegIter si;
@@ -536,7 +533,6 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     const uint32_t bar_full_a = bar(BAR_FULL_A + h), bar_empty_a = bar(BAR_EMPTY_A + h);
     RingPos rp{0, 0}, ap{0, 0};
     int seg = 0;
-    FB2_STAMP(0);
     ptx::grid_dependency_wait();          // before the first global write / scratch access
     FB2_TL(2);
     bool tl_first = true;
@@ -588,13 +584,11 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       // ------------------------------------------------ epilogue of this tile segment
       const int r_begin = sg.r0, r_end = sg.r1;                  // [r_begin, r_end) of [0, upt)
       const int blk = sg.blk, tile = sg.tile, tau = sg.blk * n_tiles + sg.tile;
-      FB2_STAMP(2);
       FB2_TL(4);
       FB2_MARK(400 + seg);
       ptx::mbar_wait(bar(BAR_ACC), seg & 1);
       FB2_MARK(410 + seg);
       FB2_TL(5);
-      FB2_STAMP(3);
       seg++;
       ptx::tc_fence_after();
       // The accumulator is read in chunks of CH columns (activation rows) so that the same code
@@ -651,18 +645,27 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         }
         const size_t row_off = (size_t)(h * HALF + ch * CH) * kTileN + nl;
         if (owner) {
-          // contributors outermost, rows unrolled inside: CH * NACC independent L2 loads in flight
-          for (int c = c_first + 1; c <= c_last; c++) {
-            const float *src = p.partials + (size_t)c * kPart + row_off;
-            float t[NACC][CH];
+          // UC contributors x CH rows x NACC accumulators of independent L2 loads in flight; the sums
+          // are taken in contributor order (deterministic)
+          constexpr int UC = NACC * CH <= 8 ? 4 : (NACC * CH <= 16 ? 2 : 1);
+#pragma unroll 1
+          for (int c0 = c_first + 1; c0 <= c_last; c0 += UC) {
+            float t[UC][NACC][CH];
 #pragma unroll
-            for (int a = 0; a < NACC; a++)
+            for (int i = 0; i < UC; i++) {
+              const float *src = p.partials + (size_t)(c0 + i) * kPart + row_off;
 #pragma unroll
-              for (int j = 0; j < CH; j++) t[a][j] = __ldcg(src + (size_t)(a * NB + j) * kTileN);
+              for (int a = 0; a < NACC; a++)
 #pragma unroll
-            for (int a = 0; a < NACC; a++)
+                for (int j = 0; j < CH; j++)
+                  t[i][a][j] = c0 + i <= c_last ? __ldcg(src + (size_t)(a * NB + j) * kTileN) : 0.0f;
+            }
 #pragma unroll
-              for (int j = 0; j < CH; j++) v[a][j] += t[a][j];
+            for (int i = 0; i < UC; i++)
+#pragma unroll
+              for (int a = 0; a < NACC; a++)
+#pragma unroll
+                for (int j = 0; j < CH; j++) v[a][j] += t[i][a][j];
           }
         }
         if (whole || owner) {
@@ -685,18 +688,11 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       if (lane == 0) ptx::mbar_arrive(bar(BAR_ACC_EMPTY));      // accumulators may be overwritten
       FB2_TL(6);
       if (!whole && !owner) {
-        FB2_STAMP(4);
         ptx::named_bar_sync(1, kDequantWarps * 32);              // every partial store of the CTA is issued
         if (threadIdx.x == 0) ptx::red_release_add(p.counters + tau, 1);
         __syncwarp();
-        FB2_STAMP(5);
       }
     }
-#ifdef FB2_TIMELINE
-    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1)
-      printf("fb2 timeline cta %d units %lld: setup %lld first_full %lld dequant_done %lld acc %lld partial_stored %lld "
-             "atomic_done %lld reduce_done %lld\n", cta, u1 - u0, tl[0], tl[1], tl[2], tl[3], tl[4], tl[5], tl[6]);
-#endif
   }
 
   // -------------------------------------------------------------------------- teardown

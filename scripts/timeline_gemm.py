@@ -30,7 +30,7 @@ torch.cuda.synchronize()
 print(f"K={k} N={n} M={m} act={act}: graph of {NL} GEMMs {e0.elapsed_time(e1) * 1e3 / NL:.2f} us per GEMM (with trace stores)")
 d = dbg.numpy()[296 * 32:].reshape(NL, 296, 32)
 t0 = d[0, :, 0][d[0, :, 0] > 0].min()
-names = ["entry", "setup", "gdc", "data0", "loop_end", "acc", "epi_end", "exit"]
+names = ["entry", "setup", "gdc", "data0", "loop_end", "acc", "epi_end", "exit", "units", "fix_end"]
 for L in range(NL):
     a = d[L]
     live = a[:, 0] > 0
@@ -40,4 +40,15 @@ for L in range(NL):
         v = v[v > 0] - t0
         row[nm] = (int(v.min()), int(np.median(v)), int(v.max())) if len(v) else None
     print(f"launch {L}: ctas {int(live.sum())} units/cta {int(a[live, 8].max())}  " +
-          "  ".join(f"{nm}={row[nm][0]}/{row[nm][1]}/{row[nm][2]}" for nm in names if row[nm]))
+          "  ".join(f"{nm}={row[nm][0]}/{row[nm][1]}/{row[nm][2]}" for nm in names if row[nm] and nm != "units"))
+
+if os.environ.get("TL_PER_CTA"):
+    a = d[4]
+    dur = (a[:, 4] - a[:, 2]) / 1e3          # gdc -> loop_end of the last segment, us
+    sm = a[:, 10]
+    order = np.argsort(sm, kind="stable")
+    print("per SM (smid: cta ids -> loop us):")
+    for smid in sorted(set(sm.tolist()))[:40]:
+        ids = [int(c) for c in np.where(sm == smid)[0]]
+        print(f"  sm {int(smid):3d}: " + "  ".join(f"cta {c:3d} units {int(a[c, 8])} entry {int(a[c,0]-t0)/1e3:.1f} loop {dur[c]:.1f}" for c in ids))
+    print("loop us by cta id (first 296):", np.round(dur, 1).tolist())
