@@ -224,6 +224,36 @@ __global__ void permute_cols_kernel(const __half *__restrict__ x, const int32_t 
   for (int r = blockIdx.y; r < m; r += gridDim.y) xp[(size_t)r * k + j] = x[(size_t)r * k + src];
 }
 
+// Batched (prefill) form: one CTA per activation row.  The row is staged in shared memory with
+// 16-byte loads and written back permuted with 16-byte stores, so global traffic is exactly one
+// read and one write of x (the element-wise kernel above moves 2 bytes per 32-byte sector).
+__global__ void __launch_bounds__(256) permute_rows_kernel(const __half *__restrict__ x,
+                                                           const int32_t *__restrict__ perm,
+                                                           __half *__restrict__ xp, int m, int k) {
+  extern __shared__ __align__(16) __half s_row[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int k8 = k >> 3;                                         // k % 8 == 0 (checked by the launcher)
+  for (int r = blockIdx.x; r < m; r += gridDim.x) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(x + (size_t)r * k);
+    for (int i = threadIdx.x; i < k8; i += blockDim.x) reinterpret_cast<uint4 *>(s_row)[i] = src[i];
+    __syncthreads();
+    uint4 *dst = reinterpret_cast<uint4 *>(xp + (size_t)r * k);
+    for (int i = threadIdx.x; i < k8; i += blockDim.x) {
+      const int4 p0 = reinterpret_cast<const int4 *>(perm)[2 * i];
+      const int4 p1 = reinterpret_cast<const int4 *>(perm)[2 * i + 1];
+      const unsigned short *sr = reinterpret_cast<const unsigned short *>(s_row);
+      uint4 o;
+      o.x = (uint32_t)sr[p0.x] | ((uint32_t)sr[p0.y] << 16);
+      o.y = (uint32_t)sr[p0.z] | ((uint32_t)sr[p0.w] << 16);
+      o.z = (uint32_t)sr[p1.x] | ((uint32_t)sr[p1.y] << 16);
+      o.w = (uint32_t)sr[p1.z] | ((uint32_t)sr[p1.w] << 16);
+      dst[i] = o;
+    }
+    __syncthreads();
+  }
+}
+
 template <bool kGelu>
 __global__ void act_mul_split_kernel(const __half *__restrict__ gu, __half *__restrict__ out,
                                      size_t tokens, size_t im) {
@@ -290,7 +320,6 @@ int launch_permute_cols(const __half *x, const int32_t *perm, __half *xp, int m,
                         cudaStream_t stream) {
   if (m <= 0) return FB2_OK;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((k + 255) / 256, m < 64 ? m : 64);
   cfg.blockDim = dim3(256);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -298,6 +327,17 @@ int launch_permute_cols(const __half *x, const int32_t *perm, __half *xp, int m,
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  const size_t row_bytes = (size_t)k * sizeof(__half);
+  const bool aligned = k % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)xp % 16) == 0 && ((uintptr_t)perm % 16) == 0;
+  if (m >= 16 && aligned && row_bytes <= 48 * 1024) {
+    // batched rows: one CTA per row through shared memory
+    cfg.gridDim = dim3(m < 1184 ? m : 1184);
+    cfg.dynamicSmemBytes = row_bytes;
+    FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, permute_rows_kernel, x, perm, xp, m, k));
+    count_launch();
+    return FB2_OK;
+  }
+  cfg.gridDim = dim3((k + 255) / 256, m < 64 ? m : 64);
   FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, permute_cols_kernel, x, perm, xp, m, k));
   count_launch();
   return FB2_OK;

@@ -16,7 +16,7 @@ reps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 act = bool(int(sys.argv[5])) if len(sys.argv) > 5 else True
 rng = np.random.default_rng(0)
 lins = []
-for i in range(3):
+for i in range(int(os.environ.get("PROF_LINEARS", "3"))):
     qw, sc, qz, gi = bench.synth_gptq(rng, k, n, act_order=act)
     lins.append(fb2.GptqLinear.from_raw(qw, sc, qz, gi, None, 4, 128, k, n))
 fb2.pregrow_scratch(0, max(m, 64))
