@@ -1164,10 +1164,18 @@ int fb2_moe_ffn_forward(const fb2_stack_t *gate_up, const fb2_stack_t *down, fb2
                                 ids, wts, sorted, block_ids, total, (__half *)act, (__half *)dn, batch, top_k,
                                 norm_topk_prob, L.cap, sc, sms, (cudaStream_t)stream);
   }
-  // 1. route (dispatch.rs:1645)
-  if ((rc = fb2_moe_route_topk_softmax(stream, router_logits, ids, wts, batch, E, top_k, norm_topk_prob))) return rc;
-  // 2. align with pair ids: A row = id / top_k (gather fused), C row = id (dispatch.rs:1998-2009)
-  if ((rc = fb2_moe_align_block_size(stream, ids, sorted, block_ids, total, pairs, E, kFfnBlock, L.cap, 1))) return rc;
+  if (route_align_small_supported((int)batch, (int)E, (int)top_k)) {
+    // 1+2 for decode batches: routing and block alignment in one single-CTA launch
+    FB2_CUDA_TRY(cudaSetDevice(gate_up->device));
+    if ((rc = launch_route_align_small((const __half *)router_logits, ids, wts, sorted, block_ids, total, (int)batch,
+                                       (int)E, (int)top_k, norm_topk_prob, kFfnBlock, (int)L.cap,
+                                       (cudaStream_t)stream))) return rc;
+  } else {
+    // 1. route (dispatch.rs:1645)
+    if ((rc = fb2_moe_route_topk_softmax(stream, router_logits, ids, wts, batch, E, top_k, norm_topk_prob))) return rc;
+    // 2. align with pair ids: A row = id / top_k (gather fused), C row = id (dispatch.rs:1998-2009)
+    if ((rc = fb2_moe_align_block_size(stream, ids, sorted, block_ids, total, pairs, E, kFfnBlock, L.cap, 1))) return rc;
+  }
   // 3+4. gate-up grouped GEMM with SwiGLU epilogue -> act [pairs, I]
   if ((rc = fb2_gptq_stack_gemm_routed_silu(gate_up, stream, x, sorted, block_ids, total, act, batch,
                                             kFfnBlock, top_k, L.cap))) return rc;

@@ -118,6 +118,11 @@ int launch_silu_mul_split(const __half *gu, __half *out, size_t tokens, size_t i
 // moe_kernels.cu
 int launch_route_topk_softmax(const __half *logits, int32_t *ids, float *wts, int batch,
                               int num_experts, int top_k, int norm, cudaStream_t stream);
+// routing + block alignment (pair ids) of a decode batch in one single-CTA launch
+bool route_align_small_supported(int batch, int num_experts, int top_k);
+int launch_route_align_small(const __half *logits, int32_t *ids, float *wts, int32_t *sorted_ids,
+                             int32_t *block_ids, int32_t *total_post_pad, int batch, int num_experts, int top_k,
+                             int norm, int block_size, int sorted_max, cudaStream_t stream);
 int launch_build_pairs(const int32_t *expert_ids, int32_t *pairs_by_token,
                        int32_t *packed_token_idx, int32_t *expert_offsets, int pairs,
                        int num_experts, int top_k, cudaStream_t stream);

@@ -208,6 +208,118 @@ align_block_size_kernel(const int32_t *__restrict__ expert_ids,
   }
 }
 
+// Decode batches (<= 32 tokens): routing AND block alignment in ONE single-CTA launch.
+// Warp r routes token r exactly as router_kernel does (same arithmetic, same tie rule), then the
+// block builds the moe_align_block_size outputs with pair ids from a per-expert bit mask of the
+// tokens that selected it: the rank of pair (r, e) inside expert e's run is popc(mask[e] & ((1 << r) - 1)),
+// i.e. ascending pair order (the deterministic order of the host plan), with no sort and no
+// cross-CTA scan.  Replaces two dependent launches (router_kernel + align_block_size_kernel).
+constexpr int kRouteAlignThreads = 1024;
+__global__ void __launch_bounds__(kRouteAlignThreads)
+route_align_small_kernel(const __half *__restrict__ logits, int32_t *__restrict__ out_ids, float *__restrict__ out_w,
+                         int32_t *__restrict__ sorted_ids, int32_t *__restrict__ block_ids,
+                         int32_t *__restrict__ total_post_pad, int batch, int num_experts, int top_k, int norm,
+                         int block_size, int sorted_max) {
+  extern __shared__ float s_probs[];                  // [32 warps][num_experts]
+  __shared__ unsigned s_mask[kMaxExperts];            // tokens that selected expert e
+  __shared__ int s_off[kMaxExperts + 1];              // padded start of expert e's run
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  for (int i = threadIdx.x; i < num_experts; i += kRouteAlignThreads) s_mask[i] = 0u;
+  __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pairs = batch * top_k;
+  if (warp < batch) {
+    const int row = warp;
+    float *probs = s_probs + (size_t)warp * num_experts;
+    float tmax = -INFINITY;
+    for (int i = lane; i < num_experts; i += 32) {
+      float v = __half2float(logits[(size_t)row * num_experts + i]);
+      probs[i] = v;
+      tmax = v > tmax ? v : tmax;
+    }
+    for (int o = 16; o; o >>= 1) {
+      float t = __shfl_xor_sync(0xffffffffu, tmax, o);
+      tmax = t > tmax ? t : tmax;
+    }
+    __syncwarp();
+    for (int i = lane; i < num_experts; i += 32) probs[i] = expf(probs[i] - tmax);
+    __syncwarp();
+    float sum = 0.f;
+    if (lane == 0)
+      for (int i = 0; i < num_experts; i++) sum += probs[i];   // left to right, as router.rs:150-155
+    sum = __shfl_sync(0xffffffffu, sum, 0);
+    const float inv = 1.0f / sum;
+    for (int i = lane; i < num_experts; i += 32) probs[i] *= inv;
+    __syncwarp();
+    float sel_sum = 0.f, my_w = 0.f;
+    for (int k = 0; k < top_k; k++) {
+      float best = -INFINITY;
+      int best_i = 0x7fffffff;
+      for (int i = lane; i < num_experts; i += 32) {
+        float v = probs[i];
+        if (v > best) { best = v; best_i = i; }
+      }
+      for (int o = 16; o; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+      }
+      if (best_i == 0x7fffffff) best_i = 0;
+      if (lane == 0) {
+        out_ids[(size_t)row * top_k + k] = best_i;
+        probs[best_i] = -INFINITY;
+        atomicOr(&s_mask[best_i], 1u << row);
+      }
+      if ((k & 31) == lane) my_w = best;                // lane k keeps weight k (top_k <= 32 per pass)
+      sel_sum += best;
+      __syncwarp();
+      if ((k & 31) == 31 || k == top_k - 1) {           // flush up to 32 weights
+        const int kk = (k & ~31) + lane;
+        if (kk <= k) out_w[(size_t)row * top_k + kk] = my_w;
+      }
+    }
+    if (norm) {
+      __syncwarp();
+      for (int k = lane; k < top_k; k += 32) {
+        if (sel_sum > 0.f) out_w[(size_t)row * top_k + k] *= (1.0f / sel_sum);
+        else out_w[(size_t)row * top_k + k] = 1.0f / (float)top_k;
+      }
+    }
+  }
+  __syncthreads();
+  // padded offsets: warp 0 scans the experts 32 at a time
+  if (warp == 0) {
+    int carry = 0;
+    for (int e0 = 0; e0 < num_experts; e0 += 32) {
+      const int e = e0 + lane;
+      const int cnt = e < num_experts ? __popc(s_mask[e]) : 0;
+      const int padded = ((cnt + block_size - 1) / block_size) * block_size;
+      int incl = padded;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (e < num_experts) s_off[e] = carry + incl - padded;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) { s_off[num_experts] = carry; total_post_pad[0] = carry; }
+  }
+  __syncthreads();
+  const int total = min(s_off[num_experts], sorted_max);
+  for (int i = threadIdx.x; i < total; i += kRouteAlignThreads) sorted_ids[i] = pairs;   // sentinel
+  for (int e = threadIdx.x; e < num_experts; e += kRouteAlignThreads)
+    for (int b = s_off[e] / block_size; b < s_off[e + 1] / block_size; b++) block_ids[b] = e;
+  __syncthreads();
+  for (int pidx = threadIdx.x; pidx < pairs; pidx += kRouteAlignThreads) {
+    const int row = pidx / top_k;
+    const int e = out_ids[pidx];                        // written by this CTA (visible after the barrier)
+    const int slot = s_off[e] + __popc(s_mask[e] & ((1u << row) - 1u));
+    if (slot < sorted_max) sorted_ids[slot] = pidx;
+  }
+}
+
 template <bool kPairs>
 __global__ void combine_kernel(const __half *__restrict__ rows, const int32_t *__restrict__ pairs_by_token,
                                const float *__restrict__ weights, __half *__restrict__ out,
@@ -256,6 +368,21 @@ int launch_route_topk_softmax(const __half *logits, int32_t *ids, float *wts, in
   if (batch <= 0) return FB2_OK;
   return launch_pdl(router_kernel, dim3(batch), dim3(32), (size_t)num_experts * sizeof(float), stream, logits, ids,
                     wts, batch, num_experts, top_k, norm);
+}
+
+bool route_align_small_supported(int batch, int num_experts, int top_k) {
+  return batch >= 1 && batch <= 32 && num_experts <= kMaxExperts && top_k <= num_experts &&
+         (size_t)32 * num_experts * sizeof(float) <= 160 * 1024;
+}
+
+int launch_route_align_small(const __half *logits, int32_t *ids, float *wts, int32_t *sorted_ids,
+                             int32_t *block_ids, int32_t *total_post_pad, int batch, int num_experts, int top_k,
+                             int norm, int block_size, int sorted_max, cudaStream_t stream) {
+  const size_t smem = (size_t)32 * num_experts * sizeof(float);
+  if (smem > 48 * 1024)
+    FB2_CUDA_TRY(cudaFuncSetAttribute(route_align_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return launch_pdl(route_align_small_kernel, dim3(1), dim3(kRouteAlignThreads), smem, stream, logits, ids, wts,
+                    sorted_ids, block_ids, total_post_pad, batch, num_experts, top_k, norm, block_size, sorted_max);
 }
 
 int launch_build_pairs(const int32_t *expert_ids, int32_t *pairs_by_token,
