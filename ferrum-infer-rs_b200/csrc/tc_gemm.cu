@@ -99,6 +99,7 @@ struct TcParams {
   int tiles_per_expert;   // ld / 128
   int ld_out;             // output row stride
   int x_tma;              // activations come through the 2-D tensor map (dense / dispatch rows)
+  int whole_tiles;        // dense / dispatch rows: CTA ranges are cut on tile boundaries (host decision)
 };
 
 // barrier slots (8 bytes each)
@@ -176,6 +177,17 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, float *v) {
 
 // ---- stream-K bookkeeping (identical in every role) -------------------------------------
 __device__ __forceinline__ long long range_start(long long c, long long T, int G) { return c * T / G; }
+// Tiles of only a few units (K <= 1024: the MoE down projection has 6) are never split: cutting one
+// costs a partial-tile fix-up (~3 us) that is longer than streaming the whole tile.  CTA c then owns
+// the whole tiles [c * NT / G, (c + 1) * NT / G) -- when that balances: at most one tile per CTA, or so
+// many that a difference of one tile is small (measured on the Qwen3 MoE down projection).
+constexpr int kWholeTileMaxUnits = 8;
+__host__ __device__ __forceinline__ bool whole_tile_mode(int upt, long long n_tiles_total, int slots) {
+  return upt <= kWholeTileMaxUnits && (n_tiles_total <= slots || n_tiles_total >= 4LL * slots);
+}
+__device__ __forceinline__ long long tile_range_start(long long c, long long NT, int G, int upt) {
+  return (c * NT / G) * upt;
+}
 __device__ __forceinline__ int cta_of_unit(long long u, long long T, int G) {
   long long c = u * G / T;
   while (c + 1 < G && range_start(c + 1, T, G) <= u) c++;
@@ -275,8 +287,13 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   long long T = 0, u0 = 0, u1 = 0;
   if (!routed) {
     T = (long long)rowmap_num_blocks(p.rm, NB) * n_tiles * upt;
-    u0 = range_start(cta, T, G);
-    u1 = range_start(cta + 1, T, G);
+    if (p.whole_tiles) {                                         // host decided (it sized the grid)
+      u0 = tile_range_start(cta, T / upt, G, upt);
+      u1 = tile_range_start(cta + 1, T / upt, G, upt);
+    } else {
+      u0 = range_start(cta, T, G);
+      u1 = range_start(cta + 1, T, G);
+    }
     if (u0 >= u1) return;                                        // CTA-uniform, before any barrier
   }
 
@@ -322,11 +339,18 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     // The grid was sized for the worst-case block count; with fewer units only the first
     // max(1, T/2) CTAs take part, so that every participating CTA owns a non-empty range and the
     // contributors of a tile are exactly the consecutive CTAs c_first .. c_last.
-    const long long g_eff = T / 2 > 1 ? T / 2 : 1;
+    const bool whole_tiles = whole_tile_mode(upt, T / upt, G);
+    const long long cap = whole_tiles ? T / upt : T / 2;           // whole tiles | >= 2 units per CTA
+    const long long g_eff = cap > 1 ? cap : 1;
     if (g_eff < G) G = (int)g_eff;
     if (cta < G) {
-      u0 = range_start(cta, T, G);
-      u1 = range_start(cta + 1, T, G);
+      if (whole_tiles) {
+        u0 = tile_range_start(cta, T / upt, G, upt);
+        u1 = tile_range_start(cta + 1, T / upt, G, upt);
+      } else {
+        u0 = range_start(cta, T, G);
+        u1 = range_start(cta + 1, T, G);
+      }
     }
   }
   const bool idle = u0 >= u1;                                    // routed launch with fewer units than CTAs
@@ -924,7 +948,7 @@ moe_ffn_fused_kernel(const TcParams p1, const TcParams p2, const MoeFusedArgs m)
 
 // ------------------------------------------------------------------------ host planning
 struct TcPlan {
-  int nb, row_blocks, n_tiles, nacc, grid;
+  int nb, row_blocks, n_tiles, nacc, grid, whole_tiles;
   size_t partial_floats, counters;
   uint32_t smem;
 };
@@ -960,7 +984,9 @@ TcPlan make_plan(const WeightRef &w, const RowMap &rows, int epilogue, int sm_co
   static const int ctas_per_sm_dbg = [] { const char *e = getenv("FB2_DEBUG_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   const int per_sm = ctas_per_sm_dbg ? ctas_per_sm_dbg : (pl.nb >= 128 ? 1 : 2);
   const int slots = per_sm * (sm_count > 0 ? sm_count : 148);
-  long long g = units / 2;                       // >= 2 units per CTA: amortise setup / epilogue
+  const int upt = pl.nacc * (w.k / kGroup);
+  pl.whole_tiles = rows.mode != ROWS_ROUTED && whole_tile_mode(upt, units / upt, slots);
+  long long g = pl.whole_tiles ? units / upt : units / 2;         // whole tiles | >= 2 units per CTA
   if (g < 1) g = 1;
   pl.grid = (int)(g < slots ? g : slots);
   pl.partial_floats = (size_t)pl.grid * pl.nacc * pl.nb * kTileN;
@@ -1099,6 +1125,7 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   p.groups = w.k / kGroup;
   p.tiles_per_expert = w.ld / kTileN;
   p.ld_out = epilogue ? w.n / 2 : w.n;
+  p.whole_tiles = pl.whole_tiles;
   // Rows that are contiguous in x (dense batches, dispatch entries) come through a 2-D TMA tensor
   // map: one instruction per [NB x 64] box instead of NB*16 cp.async.  Routed rows are gathered.
   CUtensorMap xmap;
