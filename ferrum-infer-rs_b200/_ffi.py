@@ -76,6 +76,21 @@ SIGNATURES = {
     "fb2_fused_gelu_tanh_mul_split": (_i32, [_vp, _vp, _vp, _sz, _sz]),
     "fb2_moe_ffn_workspace_bytes": (_sz, [_vp, _vp, _sz, _sz]),
     "fb2_moe_ffn_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _i32, _vp, _sz]),
+    "fb2_gptq_shard_dims": (_i32, [_sz, _sz, _sz, _i32, _i32, _i32, _vp, _i32, C.POINTER(_sz), C.POINTER(_sz)]),
+    "fb2_gptq_shard_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _sz, _i32, _i32, _i32, _vp, _i32,
+                                   _vp, _vp, _vp, _vp, _vp]),
+    "fb2_gptq_linear_create_sharded": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _sz, _sz, _sz, _i32, _i32, _i32, _i32,
+                                              _vp, _i32, _vp, C.POINTER(_vp)]),
+    "fb2_comm_get_unique_id": (_i32, [_vp]),
+    "fb2_comm_init_rank": (_i32, [_vp, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "fb2_comm_destroy": (None, [_vp]),
+    "fb2_comm_world_size": (_i32, [_vp]),
+    "fb2_comm_rank": (_i32, [_vp]),
+    "fb2_all_reduce_f16": (_i32, [_vp, _vp, _vp, _sz]),
+    "fb2_all_gather_f16": (_i32, [_vp, _vp, _vp, _vp, _sz]),
+    "fb2_broadcast_f16": (_i32, [_vp, _vp, _vp, _sz, _i32]),
+    "fb2_all_to_all_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fb2_gptq_linear_forward_allreduce": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz]),
 }
 
 _lib = None

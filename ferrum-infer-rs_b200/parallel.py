@@ -111,11 +111,119 @@ def _default_qkv_segments(n: int) -> List[int]:
     return table.get(n, [n])
 
 
-def all_reduce_(t):
-    """Sum all-reduce of a partial [M, N] f16 output, in place (nccl_comm.rs:40-48)."""
+def all_reduce_(t, comm=None):
+    """Sum all-reduce of a partial [M, N] f16 output, in place (nccl_comm.rs:40-48): through the
+    library's own communicator when one is given, else torch.distributed."""
+    if comm is not None:
+        comm.all_reduce_(t)
+        return t
     import torch.distributed as dist
     dist.all_reduce(t)
     return t
+
+
+# ------------------------------------------------------------------------------------------
+# The C-ABI side of the same logic (csrc/parallel.cu): host sharding in C++, NCCL communicator.
+# ------------------------------------------------------------------------------------------
+SPLIT_COLUMN, SPLIT_ROW = 0, 1
+
+
+def shard_host(qweight, scales, qzeros, g_idx, bias, group: int, k: int, n: int, split: int, rank: int,
+               world: int, segments: Optional[Sequence[int]] = None):
+    """fb2_gptq_shard_host: the library's C++ statement of column_shard() / row_shard().
+    Returns (qweight, scales, qzeros, bias, x_cols, k_local, n_local).  Pure host code."""
+    import ctypes as C
+    from ._ffi import lib, check
+    qw = np.ascontiguousarray(qweight, dtype=np.int32)
+    sc = np.ascontiguousarray(scales, dtype=np.float32)
+    qz = np.ascontiguousarray(qzeros, dtype=np.int32)
+    gi = None if g_idx is None else np.ascontiguousarray(g_idx, dtype=np.int32)
+    bs = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    seg = None if not segments else (C.c_size_t * len(segments))(*[int(v) for v in segments])
+    kl, nl = C.c_size_t(0), C.c_size_t(0)
+    check(lib().fb2_gptq_shard_dims(k, n, group, split, rank, world, seg, len(segments) if segments else 0,
+                                    C.byref(kl), C.byref(nl)))
+    kl, nl = kl.value, nl.value
+    qw_o = np.empty((kl // 8, nl), dtype=np.int32)
+    sc_o = np.empty((kl // group, nl), dtype=np.float32)
+    qz_o = np.empty((kl // group, nl // 8), dtype=np.int32)
+    bs_o = np.empty(nl, dtype=np.float32) if bs is not None else None
+    xc_o = np.empty(kl, dtype=np.int32)
+    ptr = lambda a: None if a is None else a.ctypes.data
+    check(lib().fb2_gptq_shard_host(ptr(qw), ptr(sc), ptr(qz), ptr(gi), ptr(bs), group, k, n, split, rank, world,
+                                    seg, len(segments) if segments else 0, ptr(qw_o), ptr(sc_o), ptr(qz_o),
+                                    ptr(bs_o), ptr(xc_o)))
+    return qw_o, sc_o, qz_o, bs_o, xc_o, kl, nl
+
+
+class Comm:
+    """fb2_comm_t: the library's NCCL communicator (BackendCollective, capabilities.rs:85-107).
+    `Comm.from_torch_distributed()` distributes rank 0's unique id over an already initialised
+    torch.distributed group (any backend) -- the id exchange is the only thing torch does here."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
+        import ctypes as C
+        from ._ffi import lib, check
+        assert len(unique_id) == 128
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        check(lib().fb2_comm_init_rank(buf, rank, world, device, C.byref(self._h)))
+        self.rank, self.world, self.device = rank, world, device
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from ._ffi import lib, check
+        buf = C.create_string_buffer(128)
+        check(lib().fb2_comm_get_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, device: int):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ids = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        torch.cuda.set_device(device)
+        return cls(ids[0], rank, world, device)
+
+    def _stream(self):
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+
+    def all_reduce_(self, t):
+        from ._ffi import lib, check
+        assert t.is_contiguous() and t.dtype.itemsize == 2
+        check(lib().fb2_all_reduce_f16(self._h, self._stream(), t.data_ptr(), t.numel()))
+        return t
+
+    def all_gather(self, t, out):
+        from ._ffi import lib, check
+        assert t.is_contiguous() and out.is_contiguous() and out.numel() == t.numel() * self.world
+        check(lib().fb2_all_gather_f16(self._h, self._stream(), t.data_ptr(), out.data_ptr(), t.numel()))
+        return out
+
+    def broadcast_(self, t, root=0):
+        from ._ffi import lib, check
+        check(lib().fb2_broadcast_f16(self._h, self._stream(), t.data_ptr(), t.numel(), root))
+        return t
+
+    def all_to_all_single(self, recv, send):
+        """Equal split of `send` / `recv` (f16, contiguous) over the ranks."""
+        import ctypes as C
+        from ._ffi import lib, check
+        per = send.numel() // self.world
+        arr = (C.c_size_t * self.world)
+        offs, cnts = arr(*[p * per for p in range(self.world)]), arr(*[per] * self.world)
+        check(lib().fb2_all_to_all_f16(self._h, self._stream(), send.data_ptr(), offs, cnts, recv.data_ptr(), offs, cnts))
+        return recv
+
+    def close(self):
+        from ._ffi import lib
+        if self._h:
+            lib().fb2_comm_destroy(self._h)
+            self._h = None
 
 
 # ------------------------------------------------------------------------------------------
@@ -157,10 +265,10 @@ class TensorParallelLinear:
         self.k_local, self.n_local = kl, nl
         self.linear = GptqLinear.from_raw(qw, sc, qz, gi, bias, bits, group, kl, nl, device=device)
 
-    def forward(self, x, out=None, m=None):
+    def forward(self, x, out=None, m=None, comm=None):
         y = self.linear.forward(x, out, m)
         if self.row_parallel and self.world > 1:
-            all_reduce_(y)
+            all_reduce_(y, comm)
         return y
 
     __call__ = forward

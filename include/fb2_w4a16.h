@@ -247,6 +247,80 @@ FB2_API int fb2_moe_ffn_forward(const fb2_stack_t *gate_up, const fb2_stack_t *d
                                 size_t top_k, int norm_topk_prob, void *workspace,
                                 size_t workspace_bytes);
 
+/* ------------------------------------------------------------------------------------
+ * Tensor parallelism: sharding GPTQ tensors, and the collectives that complete the sharded
+ * GEMMs.  Shard maths: crates/ferrum-engine/src/parallel/tensor_parallel.rs:171-195 and
+ * crates/ferrum-models/tests/tp_sharding_test.rs:7-170 (the reference shards dense tensors
+ * only; quantised sharding -- 8-column qzeros words, 128-row groups, act-order -- is defined
+ * here).
+ *   FB2_SPLIT_COLUMN  split N.  `segments` (widths of the parts fused along N, e.g. q|k|v or
+ *       gate|up; NULL = one part) are split separately and the rank's pieces re-fused, so
+ *       SiLU(gate)*up and the head layout stay local.  Every piece must be a multiple of 8
+ *       columns.  The shard keeps g_idx (all K rows are local).
+ *   FB2_SPLIT_ROW     split K on group boundaries; with act-order the split is taken in
+ *       g_idx-SORTED order (every rank owns whole groups and only its own scales / zeros) and
+ *       the shard has sequential groups.  x_cols[k_local] = the columns of the full activation
+ *       this shard multiplies, in the order it expects them.  The bias stays with rank 0.
+ * fb2_gptq_shard_host is pure host code (no GPU needed); outputs are caller-allocated:
+ *   qweight_out [k_local/8, n_local], scales_out [k_local/g, n_local],
+ *   qzeros_out [k_local/g, n_local/8], bias_out [n_local] (nullable), x_cols_out [k_local]
+ *   (nullable).
+ * ---------------------------------------------------------------------------------- */
+enum { FB2_SPLIT_COLUMN = 0, FB2_SPLIT_ROW = 1 };
+FB2_API int fb2_gptq_shard_dims(size_t k, size_t n, size_t group_size, int split, int tp_rank,
+                                int tp_size, const size_t *segments, int n_seg, size_t *k_local,
+                                size_t *n_local);
+FB2_API int fb2_gptq_shard_host(const int32_t *qweight, const float *scales, const int32_t *qzeros,
+                                const int32_t *g_idx, const float *bias, size_t group_size,
+                                size_t k, size_t n, int split, int tp_rank, int tp_size,
+                                const size_t *segments, int n_seg, int32_t *qweight_out,
+                                float *scales_out, int32_t *qzeros_out, float *bias_out,
+                                int32_t *x_cols_out);
+/* load_gptq of this rank's shard: fb2_gptq_shard_host + fb2_gptq_linear_create. */
+FB2_API int fb2_gptq_linear_create_sharded(const int32_t *qweight, const float *scales,
+                                           const int32_t *qzeros, const int32_t *g_idx,
+                                           const float *bias, uint32_t bits, size_t group_size,
+                                           size_t k, size_t n, int device, int tp_rank,
+                                           int tp_size, int split, const size_t *segments,
+                                           int n_seg, int32_t *x_cols_out, fb2_linear_t **out);
+
+/* Collectives.  Replaces BackendCollective::{world_size, rank, all_reduce, all_gather,
+ * broadcast} (crates/ferrum-kernels/src/backend/capabilities.rs:85-107) and NcclRank
+ * (crates/ferrum-kernels/src/backend/cuda/nccl_comm.rs:12-105): one communicator per process
+ * (= per GPU), every call is enqueued on the caller's stream, nothing synchronises.
+ * NCCL is bound at run time from the process's libnccl.so.2 (FB2_NCCL_LIB overrides the name);
+ * without it the calls return FB2_ERR_NCCL.
+ *   fb2_comm_get_unique_id   rank 0 fills 128 bytes (ncclUniqueId) for the caller to distribute
+ *   fb2_comm_init_rank       collective over all ranks (ncclCommInitRank)
+ *   fb2_all_reduce_f16       in-place sum of `len` halves (nccl_comm.rs:40 all_reduce_f16_inplace)
+ *   fb2_all_gather_f16       recv [world, len_per_rank]
+ *   fb2_all_to_all_f16       the expert-parallel dispatch / return: peer p receives
+ *                            send[send_offsets[p] .. + send_counts[p]) and this rank receives
+ *                            recv[recv_offsets[p] .. + recv_counts[p]) from it (elements; host
+ *                            arrays of world_size entries, read during the call only)
+ *   fb2_gptq_linear_forward_allreduce   row-parallel linear: partial GEMM + all-reduce
+ * ---------------------------------------------------------------------------------- */
+typedef struct fb2_comm fb2_comm_t;
+#define FB2_UNIQUE_ID_BYTES 128
+FB2_API int fb2_comm_get_unique_id(void *id_out);
+FB2_API int fb2_comm_init_rank(const void *unique_id, int rank, int world_size, int device,
+                               fb2_comm_t **out);
+FB2_API void fb2_comm_destroy(fb2_comm_t *comm);
+FB2_API int fb2_comm_world_size(const fb2_comm_t *comm);
+FB2_API int fb2_comm_rank(const fb2_comm_t *comm);
+FB2_API int fb2_all_reduce_f16(fb2_comm_t *comm, fb2_stream_t stream, fb2_half *buf, size_t len);
+FB2_API int fb2_all_gather_f16(fb2_comm_t *comm, fb2_stream_t stream, const fb2_half *send,
+                               fb2_half *recv, size_t len_per_rank);
+FB2_API int fb2_broadcast_f16(fb2_comm_t *comm, fb2_stream_t stream, fb2_half *buf, size_t len,
+                              int root);
+FB2_API int fb2_all_to_all_f16(fb2_comm_t *comm, fb2_stream_t stream, const fb2_half *send,
+                               const size_t *send_offsets, const size_t *send_counts,
+                               fb2_half *recv, const size_t *recv_offsets,
+                               const size_t *recv_counts);
+FB2_API int fb2_gptq_linear_forward_allreduce(const fb2_linear_t *lin, fb2_comm_t *comm,
+                                              fb2_stream_t stream, const fb2_half *x,
+                                              fb2_half *y, size_t m);
+
 #ifdef __cplusplus
 }
 #endif

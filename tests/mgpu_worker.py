@@ -85,9 +85,46 @@ def main():
     torch.cuda.synchronize()
     d = (y_ep.float() - y_ref[sl].float()).abs().max().item() / max(y_ref.float().abs().max().item(), 1e-6)
     assert d < 2e-3, f"EP vs single-GPU rel {d}"
+    # ---------------- the library's own communicator + C++ sharding (csrc/parallel.cu)
+    comm = par.Comm.from_torch_distributed(local)
+    assert (comm.rank, comm.world) == (rank, world)
+    t = torch.full((1000,), float(rank + 1), dtype=torch.float16, device=dev)
+    comm.all_reduce_(t)
+    torch.cuda.synchronize()
+    assert torch.all(t == world * (world + 1) / 2), "fb2_all_reduce_f16"
+    piece = torch.full((8,), float(rank), dtype=torch.float16, device=dev)
+    gathered = torch.empty(8 * world, dtype=torch.float16, device=dev)
+    comm.all_gather(piece, gathered)
+    send = torch.arange(world * 4, dtype=torch.float16, device=dev) + 100 * rank
+    recv = torch.empty_like(send)
+    comm.all_to_all_single(recv, send)
+    bc = torch.full((16,), float(rank + 7), dtype=torch.float16, device=dev)
+    comm.broadcast_(bc, root=0)
+    torch.cuda.synchronize()
+    assert gathered.view(world, 8)[:, 0].tolist() == [float(r) for r in range(world)], "fb2_all_gather_f16"
+    assert recv.view(world, 4)[:, 0].tolist() == [100.0 * r + 4 * rank for r in range(world)], "fb2_all_to_all_f16"
+    assert torch.all(bc == 7.0), "fb2_broadcast_f16"
+    # row-parallel down_proj created by fb2_gptq_linear_create_sharded, completed by
+    # fb2_gptq_linear_forward_allreduce: must equal the torch.distributed path bit for bit
+    import ctypes as C
+    ffi = importlib.import_module("ferrum-infer-rs_b200._ffi")
+    h = C.c_void_p()
+    xcols = np.empty(inter // world, dtype=np.int32)
+    arr = lambda a: np.ascontiguousarray(a).ctypes.data
+    ffi.check(ffi.lib().fb2_gptq_linear_create_sharded(arr(dn.qweight), arr(dn.scales.astype(np.float32)), arr(dn.qzeros),
+                                                        arr(gi_dn.astype(np.int32)), None, 4, g, inter, hidden, local, rank,
+                                                        world, par.SPLIT_ROW, None, 0, xcols.ctypes.data, C.byref(h)))
+    assert np.array_equal(xcols, np.asarray(t_dn.x_cols, dtype=np.int32))
+    y_c = torch.empty((m, hidden), dtype=torch.float16, device=dev)
+    ffi.check(ffi.lib().fb2_gptq_linear_forward_allreduce(h, comm._h, torch.cuda.current_stream().cuda_stream,
+                                                           act_loc.data_ptr(), y_c.data_ptr(), m))
+    torch.cuda.synchronize()
+    assert torch.equal(y_c, y_tp), "fb2_gptq_linear_forward_allreduce != TensorParallelLinear + torch all_reduce"
+    ffi.lib().fb2_gptq_linear_destroy(h)
+    comm.close()
     dist.barrier()
     if rank == 0:
-        print(f"mgpu ok: world={world} tp_rel={rel:.2e} tp_vs_oracle={st['rel']:.2e} ep_rel={d:.2e}")
+        print(f"mgpu ok: world={world} tp_rel={rel:.2e} tp_vs_oracle={st['rel']:.2e} ep_rel={d:.2e} c_abi_comm=ok")
     dist.destroy_process_group()
 
 

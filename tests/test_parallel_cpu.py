@@ -127,3 +127,70 @@ def test_row_shard_rejects_indivisible():
     with pytest.raises(AssertionError):
         par.row_shard(np.zeros((48, 8), np.int32), np.zeros((3, 8), np.float32), np.zeros((3, 1), np.int32), None,
                       384, 8, 128, 0, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# The library's own (C++) sharding, csrc/parallel.cu, against the numpy statement above.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("act", [False, True])
+def test_cxx_row_shard_matches_numpy(world, act):
+    sys.path.insert(0, ROOT)
+    import oracle
+    par = importlib.import_module("ferrum-infer-rs_b200.parallel")
+    k, n, g = 1024, 256, 128
+    syn = oracle.make_synthetic(k, n, g, 0x51AB, f16_scales=True)
+    gi = oracle.random_balanced_g_idx(k, g, 9) if act else None
+    bias = oracle.lcg_f32_array(3, n, -1.0, 1.0)
+    for rank in range(world):
+        qw, sc, qz, _, kl, cols = par.row_shard(syn.qweight, syn.scales, syn.qzeros, gi, k, n, g, rank, world)
+        cqw, csc, cqz, cb, ccols, ckl, cnl = par.shard_host(syn.qweight, syn.scales, syn.qzeros, gi, bias, g, k, n,
+                                                            par.SPLIT_ROW, rank, world)
+        assert (ckl, cnl) == (kl, n)
+        assert np.array_equal(cqw, np.asarray(qw).reshape(kl // 8, n))
+        assert np.array_equal(csc, np.asarray(sc).reshape(kl // g, n))
+        assert np.array_equal(cqz, np.asarray(qz).reshape(kl // g, n // 8))
+        assert np.array_equal(ccols, np.asarray(cols, dtype=np.int32))
+        assert np.array_equal(cb, bias if rank == 0 else np.zeros(n, np.float32))   # bias stays with rank 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_cxx_column_shard_matches_numpy(world):
+    sys.path.insert(0, ROOT)
+    import oracle
+    par = importlib.import_module("ferrum-infer-rs_b200.parallel")
+    k, g = 256, 128
+    segments = [128, 64, 64]                       # a q|k|v-like fusion
+    n = sum(segments)
+    syn = oracle.make_synthetic(k, n, g, 0xC01, f16_scales=True)
+    bias = oracle.lcg_f32_array(4, n, -1.0, 1.0)
+    for rank in range(world):
+        qw, sc, qz, nl = par.column_shard(syn.qweight, syn.scales, syn.qzeros, k, n, g, rank, world, segments)
+        cqw, csc, cqz, cb, ccols, ckl, cnl = par.shard_host(syn.qweight, syn.scales, syn.qzeros, None, bias, g, k, n,
+                                                            par.SPLIT_COLUMN, rank, world, segments)
+        assert (ckl, cnl) == (k, nl)
+        assert np.array_equal(cqw, qw) and np.array_equal(csc, sc) and np.array_equal(cqz, qz)
+        cols, off = [], 0
+        for w in segments:
+            cols.append(np.arange(off + rank * (w // world), off + (rank + 1) * (w // world)))
+            off += w
+        assert np.array_equal(cb, bias[np.concatenate(cols)])
+        assert np.array_equal(ccols, np.arange(k, dtype=np.int32))
+
+
+def test_cxx_shard_rejects_bad_splits():
+    sys.path.insert(0, ROOT)
+    import oracle
+    par = importlib.import_module("ferrum-infer-rs_b200.parallel")
+    ffi = importlib.import_module("ferrum-infer-rs_b200._ffi")
+    k, n, g = 384, 128, 128                        # 3 groups: not divisible by 2
+    syn = oracle.make_synthetic(k, n, g, 1, f16_scales=True)
+    with pytest.raises(ffi.Fb2Error) as e:
+        par.shard_host(syn.qweight, syn.scales, syn.qzeros, None, None, g, k, n, par.SPLIT_ROW, 0, 2)
+    assert e.value.code == -1                      # FB2_ERR_SHAPE
+    with pytest.raises(ffi.Fb2Error):              # 24-column pieces are fine, 12-column ones are not
+        par.shard_host(syn.qweight, syn.scales, syn.qzeros, None, None, g, k, n, par.SPLIT_COLUMN, 0, 2, [24, 104])
+    gi = np.zeros(k, dtype=np.int32)               # unbalanced act-order groups
+    with pytest.raises(ffi.Fb2Error) as e:
+        par.shard_host(syn.qweight, syn.scales, syn.qzeros, gi, None, g, k + 0, n, par.SPLIT_ROW, 0, 3)
+    assert e.value.code == -2                      # FB2_ERR_UNSUPPORTED
