@@ -110,9 +110,10 @@ def main():
     ffi = importlib.import_module("ferrum-infer-rs_b200._ffi")
     h = C.c_void_p()
     xcols = np.empty(inter // world, dtype=np.int32)
-    arr = lambda a: np.ascontiguousarray(a).ctypes.data
-    ffi.check(ffi.lib().fb2_gptq_linear_create_sharded(arr(dn.qweight), arr(dn.scales.astype(np.float32)), arr(dn.qzeros),
-                                                        arr(gi_dn.astype(np.int32)), None, 4, g, inter, hidden, local, rank,
+    keep = [np.ascontiguousarray(dn.qweight, dtype=np.int32), np.ascontiguousarray(dn.scales, dtype=np.float32),
+            np.ascontiguousarray(dn.qzeros, dtype=np.int32), np.ascontiguousarray(gi_dn, dtype=np.int32)]
+    ffi.check(ffi.lib().fb2_gptq_linear_create_sharded(keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data,
+                                                        keep[3].ctypes.data, None, 4, g, inter, hidden, local, rank,
                                                         world, par.SPLIT_ROW, None, 0, xcols.ctypes.data, C.byref(h)))
     assert np.array_equal(xcols, np.asarray(t_dn.x_cols, dtype=np.int32))
     y_c = torch.empty((m, hidden), dtype=torch.float16, device=dev)
