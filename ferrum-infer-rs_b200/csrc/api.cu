@@ -1139,31 +1139,6 @@ int fb2_moe_ffn_forward(const fb2_stack_t *gate_up, const fb2_stack_t *down, fb2
   fb2_half *dn = (fb2_half *)(ws + L.down);
   const size_t pairs = batch * top_k;
   int rc;
-  // The single-launch kernel (moe_ffn_fused_kernel) is opt-in (FB2_FUSED_MOE=1): measured on B200 it
-  // is slower than the five PDL-chained launches below at every decode batch.
-  static const bool use_fused = [] { const char *e = getenv("FB2_FUSED_MOE"); return e && e[0] == '1'; }();
-  if (use_fused && moe_fused_supported(gate_up->w, down->w, batch, top_k) && top_k <= E) {
-    // decode batches: the whole layer in one persistent launch (route, align, both grouped GEMMs,
-    // SwiGLU, combine) -- see moe_ffn_fused_kernel
-    FB2_CUDA_TRY(cudaSetDevice(gate_up->device));
-    int sms = 0;
-    TcScratch sc = current_scratch(gate_up->device, &sms);
-    size_t pb = 0, nc = 0;
-    moe_fused_requirements(gate_up->w, down->w, batch, top_k, sms, &pb, &nc);
-    if (pb > sc.partial_bytes || nc > sc.num_counters) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      FB2_CUDA_TRY(cudaStreamIsCapturing((cudaStream_t)stream, &cs));
-      if (cs != cudaStreamCaptureStatusNone) {
-        set_error("scratch too small for the fused MoE kernel and the stream is capturing: call fb2_pregrow_scratch first");
-        return FB2_ERR_ARG;
-      }
-      if ((rc = grow_scratch(gate_up->device, pb, nc))) return rc;
-      sc = current_scratch(gate_up->device, &sms);
-    }
-    return launch_moe_ffn_fused(gate_up->w, down->w, (const __half *)x, (const __half *)router_logits, (__half *)out,
-                                ids, wts, sorted, block_ids, total, (__half *)act, (__half *)dn, batch, top_k,
-                                norm_topk_prob, L.cap, sc, sms, (cudaStream_t)stream);
-  }
   if (route_align_small_supported((int)batch, (int)E, (int)top_k)) {
     // 1+2 for decode batches: routing and block alignment in one single-CTA launch
     FB2_CUDA_TRY(cudaSetDevice(gate_up->device));

@@ -149,13 +149,5 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
                    size_t x_rows, __half *y, int epilogue, const TcScratch &scratch, int sm_count,
                    cudaStream_t stream);
 const char *tc_kernel_name(const WeightRef &w, size_t m);
-// Fused single-launch MoE FFN (decode batches)
-bool moe_fused_supported(const WeightRef &gu, const WeightRef &dn, size_t batch, size_t top_k);
-void moe_fused_requirements(const WeightRef &gu, const WeightRef &dn, size_t batch, size_t top_k, int sm_count,
-                            size_t *partial_bytes, size_t *counters);
-int launch_moe_ffn_fused(const WeightRef &gu, const WeightRef &dn, const __half *x, const __half *logits,
-                         __half *out, int32_t *ids, float *wts, int32_t *sorted, int32_t *block_ids,
-                         int32_t *total, __half *act, __half *down_out, size_t batch, size_t top_k, int norm,
-                         size_t cap, const TcScratch &scratch, int sm_count, cudaStream_t stream);
 
 }  // namespace fb2

@@ -52,10 +52,12 @@ namespace fb2 {
 namespace {
 
 constexpr int kDequantWarps = 8;
-constexpr int kWarpTma = kDequantWarps;             // 8
-constexpr int kWarpMma = kDequantWarps + 1;         // 9
-constexpr int kThreads = (kDequantWarps + 2) * 32;  // 320
-constexpr int kMaxStages = 8;
+constexpr int kWarpW = kDequantWarps;               // 8: weight producer
+constexpr int kWarpMma = kDequantWarps + 1;         // 9: MMA issuer
+constexpr int kWarpX = kDequantWarps + 2;           // 10: activation producer
+constexpr int kThreads = (kDequantWarps + 3) * 32;  // 352
+constexpr int kMaxWStages = 16;
+constexpr int kMaxXSlots = 4;
 constexpr int kMaxASlots = 4;
 
 // Two resource classes.  NB <= 64 ("decode"): two CTAs per SM, 256 TMEM columns each
@@ -80,11 +82,19 @@ struct StageCfg {
   static constexpr int kTmemABase = kWide ? 256 : 128;
   static constexpr int kASlots = kWide ? 4 : 2;                               // slots of one 128-k group (64 columns)
   static constexpr int kSmemBudget = kWide ? 225 * 1024 : 108 * 1024;         // per CTA
+  // Two rings.  The WEIGHT ring (HBM stream, ~3 us loaded latency) is deep and a stage is released
+  // as soon as the dequant warps have read it into registers; the ACTIVATION ring (L2 hits) is
+  // shallow and a slot lives until the MMAs that read it have completed.  With one combined ring a
+  // weight stage stayed occupied until its MMA committed, and the bytes in flight per SM -- not
+  // the dequant rate -- bounded the stream at ~4 TB/s (the same kernel on L2-resident weights ran
+  // 2.9x faster).
   static constexpr int kXBytes = NB * 256;                                    // [2 atoms][NB][128 B]
-  static constexpr int kStride = (kXBytes + kStageBytes + 1023) & ~1023;      // x first (1024-aligned)
-  static constexpr int kStagesRaw = (kSmemBudget - 1024) / kStride;
-  static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStride + 1024;                 // + barriers / misc
+  static constexpr int kXSlots = kWide ? (NB >= 256 ? 2 : 3) : (NB <= 16 ? 4 : 3);
+  static constexpr int kWBase = kXSlots * kXBytes;                            // 1024-aligned
+  static constexpr int kWStagesRaw = (kSmemBudget - 1024 - kWBase) / kStageBytes;
+  static constexpr int kWStages = kWStagesRaw > kMaxWStages ? kMaxWStages : kWStagesRaw;
+  static constexpr int kBarBase = (kWBase + kWStages * kStageBytes + 127) & ~127;
+  static constexpr int kSmemBytes = kBarBase + 1024;                          // + barriers / misc
 };
 
 struct TcParams {
@@ -103,7 +113,8 @@ struct TcParams {
 };
 
 // barrier slots (8 bytes each)
-enum { BAR_FULL = 0, BAR_EMPTY = kMaxStages, BAR_FULL_A = 2 * kMaxStages,
+enum { BAR_FULL_W = 0, BAR_EMPTY_W = kMaxWStages, BAR_FULL_X = 2 * kMaxWStages,
+       BAR_EMPTY_X = BAR_FULL_X + kMaxXSlots, BAR_FULL_A = BAR_EMPTY_X + kMaxXSlots,
        BAR_EMPTY_A = BAR_FULL_A + 2 * kMaxASlots, BAR_ACC = BAR_EMPTY_A + 2 * kMaxASlots,
        BAR_ACC_EMPTY = BAR_ACC + 1, BAR_COUNT = BAR_ACC_EMPTY + 1 };
 static_assert(BAR_COUNT * 8 <= 512, "barrier area too small");
@@ -261,18 +272,15 @@ __device__ __forceinline__ long long fb2_gtime() { long long t; asm volatile("mo
 #define FB2_TLV(slot, v) do { } while (0)
 #endif
 
-template <int NB, bool kSilu, bool kReentrant = false>
-__device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *tbl, const CUtensorMap *xmap,
-                                        uint32_t ext_tmem = 0xFFFFFFFFu) {
-  // ext_tmem != ~0: tensor memory was allocated by the caller (the fused MoE kernel runs this body
-  // twice; a CTA may not allocate again after tcgen05.relinquish_alloc_permit)
+template <int NB, bool kSilu>
+__device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *tbl, const CUtensorMap *xmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SC = StageCfg<NB>;
   constexpr int kTmemCols = SC::kTmemCols, kTmemABase = SC::kTmemABase, kASlots = SC::kASlots;
   constexpr int NACC = kSilu ? 2 : 1;
   constexpr int HALF = NB / 2;
-  constexpr int S = SC::kStages;
-  static_assert(S >= 3, "smem ring too shallow");
+  constexpr int SW = SC::kWStages, SX = SC::kXSlots;
+  static_assert(SW >= 3 && SX >= 2, "smem rings too shallow");
   static_assert(NACC * NB <= kTmemABase, "accumulators overlap the A ring");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -298,26 +306,35 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   }
 
   const uint32_t smem_base = ptx::smem_u32(smem);
-  const uint32_t bars = smem_base + S * SC::kStride;
+  const uint32_t bars = smem_base + SC::kBarBase;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + S * SC::kStride + 512);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + SC::kBarBase + 512);
   const size_t tile_stride = (size_t)groups * kStageBytes;
 
   // ------------------------------------------------------------------ one-time setup
-  // The producer owns the stage barriers and starts streaming weights at once; TMEM
-  // allocation and the other barriers proceed in parallel on the MMA warp.
-  if (warp == kWarpTma) {
+  // Each producer owns the barriers of its ring and starts at once; TMEM allocation and the other
+  // barriers proceed in parallel on the MMA warp.  Named barrier 2: the producers only ARRIVE (they
+  // never wait for the rest of the CTA), the nine other warps sync.
+  if (warp == kWarpW) {
     if (lane == 0) {
-      for (int i = 0; i < S; i++) {
-        // one arrive.expect_tx by the producer (+ 32 cp.async arrivals when rows are gathered)
-        ptx::mbar_init(bar(BAR_FULL + i), (p.x_tma & 1) ? 1 : 1 + 32);
-        ptx::mbar_init(bar(BAR_EMPTY + i), kDequantWarps + 1);    // 8 warps + the MMA commit
+      for (int i = 0; i < SW; i++) {
+        ptx::mbar_init(bar(BAR_FULL_W + i), 1);                  // the producer's arrive.expect_tx
+        ptx::mbar_init(bar(BAR_EMPTY_W + i), kDequantWarps);     // read into registers by all 8 warps
       }
       ptx::mbar_fence_init();
     }
     __syncwarp();
-    // "stage barriers are live": the producer does not wait for TMEM allocation, the other
-    // warps do not wait for the producer's prologue (named barrier 2: arrive vs sync)
+    ptx::named_bar_arrive(2, kThreads);
+  } else if (warp == kWarpX) {
+    if (lane == 0) {
+      for (int i = 0; i < SX; i++) {
+        // one arrive.expect_tx by the producer (+ 32 cp.async arrivals when rows are gathered)
+        ptx::mbar_init(bar(BAR_FULL_X + i), (p.x_tma & 1) ? 1 : 1 + 32);
+        ptx::mbar_init(bar(BAR_EMPTY_X + i), 1);                 // the MMA commit
+      }
+      ptx::mbar_fence_init();
+    }
+    __syncwarp();
     ptx::named_bar_arrive(2, kThreads);
   } else if (warp == kWarpMma) {
     if (lane == 0) {
@@ -330,7 +347,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       ptx::mbar_fence_init();
     }
     __syncwarp();
-    if (ext_tmem == 0xFFFFFFFFu) ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(s_tmem));
+    ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(s_tmem));
   }
 
   if (routed) {
@@ -354,8 +371,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     }
   }
   const bool idle = u0 >= u1;                                    // routed launch with fewer units than CTAs
-  FB2_MARK(1);
-  if (warp == 0) { FB2_MARK2(0, T); FB2_MARK2(1, G); FB2_MARK2(2, u0); FB2_MARK2(3, u1); }
+
 
   const uint64_t pol = ptx::policy_evict_first();
   auto weight_src = [&](int blk, int tile, int phase, int g) {
@@ -364,43 +380,13 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
              ((size_t)expert * p.tiles_per_expert + p.w.col0 / kTileN + tile + (size_t)phase * n_tiles) *
                tile_stride + (size_t)g * kStageBytes;
   };
-  // PDL prologue: weight stages depend on no earlier kernel's output -> up to S of them are
-  // issued before the grid dependency (and before the rest of the CTA finished its setup).
-  int pre = 0;
-  if (warp == kWarpTma && !idle) {
-    {
-      SegIter si;
-      si.init(u0, u1, upt, n_tiles);
-      Seg sg;
-      while (pre < S && si.next(sg, upt, n_tiles)) {
-#pragma unroll 1
-        for (int a = 0; a < NACC; a++) {
-          const int g0 = max(sg.r0, a * groups) - a * groups, g1 = min(sg.r1, (a + 1) * groups) - a * groups;
-          if (g0 >= g1) continue;
-          const uint8_t *src = weight_src(sg.blk, sg.tile, a, g0);
-#pragma unroll 1
-          for (int g = g0; g < g1 && pre < S; g++, pre++, src += kStageBytes) {
-            if (ptx::elect_one()) {
-              // transaction bytes only: the arrival comes with the activation slice in the main
-              // loop, so the phase cannot complete before the activations are requested too
-              ptx::mbar_expect_tx(bar(BAR_FULL + pre), kStageBytes);
-              ptx::bulk_g2s_hint(smem_base + pre * SC::kStride + SC::kXBytes, src, kStageBytes, bar(BAR_FULL + pre), pol);
-            }
-            __syncwarp();
-          }
-        }
-      }
-    }
-  }
-
   uint32_t tmem_base = 0;
-  if (warp != kWarpTma) {
+  if (warp != kWarpW && warp != kWarpX) {
     ptx::tc_fence_before();
     ptx::named_bar_sync(2, kThreads);
     ptx::tc_fence_after();
-    tmem_base = ext_tmem == 0xFFFFFFFFu ? *s_tmem : ext_tmem;
+    tmem_base = *s_tmem;
   }
-  FB2_MARK(2);
   FB2_TL(1);
   FB2_TLV(8, u1 - u0);
 #ifdef FB2_TRACE
@@ -409,14 +395,41 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
 
   if (idle) {
     // nothing to stream; fall through to the teardown (TMEM was allocated)
-  } else if (warp == kWarpTma) {
-    // ================================================================== producer
+  } else if (warp == kWarpW) {
+    // ========================================================== weight producer (HBM stream)
+    // Weights depend on no earlier kernel: under programmatic dependent launch this warp streams
+    // ahead of griddepcontrol.wait (routed launches waited above: their expert ids are an input).
+    RingPos wp{0, 0};
+    int it = 0;
+    SegIter si;
+    si.init(u0, u1, upt, n_tiles);
+    Seg sg;
+    while (si.next(sg, upt, n_tiles)) {
+#pragma unroll 1
+      for (int a = 0; a < NACC; a++) {
+        const int g0 = max(sg.r0, a * groups) - a * groups, g1 = min(sg.r1, (a + 1) * groups) - a * groups;
+        if (g0 >= g1) continue;
+        const uint8_t *wsrc = weight_src(sg.blk, sg.tile, a, g0);
+#pragma unroll 1
+        for (int g = g0; g < g1; g++, it++, wsrc += kStageBytes, wp.advance(SW)) {
+          if (it >= SW) ptx::mbar_wait(bar(BAR_EMPTY_W + wp.st), wp.par ^ 1u);
+          if (ptx::elect_one()) {
+            const uint32_t full = bar(BAR_FULL_W + wp.st);
+            ptx::mbar_arrive_expect_tx(full, (uint32_t)kStageBytes);
+            ptx::bulk_g2s_hint(smem_base + SC::kWBase + wp.st * kStageBytes, wsrc, kStageBytes, full, pol);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == kWarpX) {
+    // ====================================================== activation producer (L2 hits)
     // the descriptor is a kernel parameter: fetch it before the grid dependency resolves
     if ((p.x_tma & 1) && lane == 0) ptx::prefetch_tensormap(xmap);
     ptx::grid_dependency_wait();
     // rows of the current block: lane i holds row i (and i + 32 for NB == 64)
     int cur_blk = -1, nchunks = 0, arow0 = -1, arow1 = -1, row0 = 0;
-    RingPos rp{0, 0};
+    RingPos xp{0, 0};
     int it = 0;
     SegIter si;
     si.init(u0, u1, upt, n_tiles);
@@ -443,33 +456,30 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       for (int a = 0; a < NACC; a++) {
         const int g0 = max(sg.r0, a * groups) - a * groups, g1 = min(sg.r1, (a + 1) * groups) - a * groups;
         if (g0 >= g1) continue;
-        const uint8_t *wsrc = weight_src(sg.blk, sg.tile, a, g0);
         const __half *xg = p.x + (size_t)g0 * kGroup;
 #pragma unroll 1
-        for (int g = g0; g < g1; g++, it++, wsrc += kStageBytes, xg += kGroup, rp.advance(S)) {
-          const uint32_t stage_addr = smem_base + rp.st * SC::kStride;
-          const uint32_t full = bar(BAR_FULL + rp.st);
-          FB2_MARK(100 + it);
-          if (it >= pre) ptx::mbar_wait(bar(BAR_EMPTY + rp.st), rp.par ^ 1u);
+        for (int g = g0; g < g1; g++, it++, xg += kGroup, xp.advance(SX)) {
+          const uint32_t slot_addr = smem_base + xp.st * SC::kXBytes;
+          const uint32_t full = bar(BAR_FULL_X + xp.st);
+          if (it >= SX) ptx::mbar_wait(bar(BAR_EMPTY_X + xp.st), xp.par ^ 1u);
           if (ptx::elect_one()) {
-            const uint32_t tx = (it >= pre ? (uint32_t)kStageBytes : 0u) + ((p.x_tma & 1) ? (uint32_t)SC::kXBytes : 0u);
-            ptx::mbar_arrive_expect_tx(full, tx);
-            if (it >= pre) ptx::bulk_g2s_hint(stage_addr + SC::kXBytes, wsrc, kStageBytes, full, pol);
+            ptx::mbar_arrive_expect_tx(full, (p.x_tma & 1) ? (uint32_t)SC::kXBytes : 0u);
             if (p.x_tma & 1) {
               // [NB rows x 64 k] boxes, hardware 128B swizzle; rows past the tensor end read as zero
-              ptx::tma_load_2d(stage_addr, xmap, g * kGroup, row0, full);
-              ptx::tma_load_2d(stage_addr + NB * 128, xmap, g * kGroup + 64, row0, full);
+              ptx::tma_load_2d(slot_addr, xmap, g * kGroup, row0, full);
+              ptx::tma_load_2d(slot_addr + NB * 128, xmap, g * kGroup + 64, row0, full);
             }
           }
           __syncwarp();
           if (!(p.x_tma & 1)) {
             // gathered activation slice: rows [0, nvalid) x 128 k, 16 chunks of 16 B per row
+            // (this IS the MoE gather x[id / top_k], dispatch.rs:1763)
             for (int ch0 = 0; ch0 < nchunks; ch0 += 32) {         // warp-uniform trip count
               const int ch = ch0 + lane;
               const int i = ch >> 4, c8 = ch & 15;
               const int ar = __shfl_sync(0xffffffffu, (NB > 32 && i >= 32) ? arow1 : arow0, i & 31);
               if (ch < nchunks) {
-                const uint32_t dst = stage_addr + (uint32_t)(c8 >> 3) * (NB * 128) + (uint32_t)i * 128 +
+                const uint32_t dst = slot_addr + (uint32_t)(c8 >> 3) * (NB * 128) + (uint32_t)i * 128 +
                                      (uint32_t)(((c8 & 7) ^ (i & 7)) << 4);
                 ptx::cp_async_16(dst, xg + (size_t)ar * p.w.k + c8 * 8);
               }
@@ -480,14 +490,13 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       }
     }
     __syncwarp();
-    FB2_MARK(199);
   } else if (warp == kWarpMma) {
     // ==================================================================== MMA issuer
     // Warp-uniform branch + elect.sync predicate: ptxas emits straight-line UTCHMMA with
     // uniform-register operands (no per-instruction election loop).
     constexpr uint32_t idesc = ptx::umma_idesc_f16(128, NB);
     const uint64_t b_desc_ring = ptx::umma_desc_kmajor_sw128(smem_base);
-    RingPos rp{0, 0}, ap{0, 0};
+    RingPos xp{0, 0}, ap{0, 0};
     int seg = 0;
     SegIter si;
     si.init(u0, u1, upt, n_tiles);
@@ -500,11 +509,10 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         const int g0 = max(sg.r0, a * groups), g1 = min(sg.r1, (a + 1) * groups);
         const uint32_t d_tmem = tmem_base + a * NB;
 #pragma unroll 1
-        for (int g = g0; g < g1; g++, rp.advance(S), ap.advance(kASlots)) {
-          FB2_MARK(200 + g);
-          ptx::mbar_wait(bar(BAR_FULL + rp.st), rp.par);          // activations (and weights) landed
+        for (int g = g0; g < g1; g++, xp.advance(SX), ap.advance(kASlots)) {
+          ptx::mbar_wait(bar(BAR_FULL_X + xp.st), xp.par);        // activation slice landed
           ptx::fence_proxy_async_smem();                          // cp.async data -> async proxy
-          const uint64_t b_desc0 = b_desc_ring + (uint64_t)((rp.st * SC::kStride) >> 4);
+          const uint64_t b_desc0 = b_desc_ring + (uint64_t)((xp.st * SC::kXBytes) >> 4);
           const uint32_t acc_flag = g != g0 ? 1u : 0u;            // first unit of a phase zero-inits
 #pragma unroll
           for (int h = 0; h < 2; h++) {
@@ -518,7 +526,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
                 ptx::umma_f16_ts(d_tmem, a_t + kk * 8, b_d + (uint64_t)(kk * 2), idesc,
                                  (h | kk) != 0 ? 1u : acc_flag);
               ptx::tc_commit(bar(BAR_EMPTY_A + ap.st * 2 + h));
-              if (h == 1) ptx::tc_commit(bar(BAR_EMPTY + rp.st)); // stage's activation slice consumed
+              if (h == 1) ptx::tc_commit(bar(BAR_EMPTY_X + xp.st)); // activation slot consumed
             }
             __syncwarp();
           }
@@ -528,34 +536,17 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       __syncwarp();
       seg++;
     }
-    // Drain: tcgen05.commit arrivals are asynchronous and nobody waits for the last use of each
-    // stage / A slot.  Wait for them here so that the barriers can be invalidated (and re-initialised
-    // by a second pass of this body in the fused MoE kernel) without racing a late arrival.
-    FB2_MARK(290);
-    if constexpr (kReentrant) {
-      const int n_units = (int)(u1 - u0);
-      for (int st = 0; st < S && st < n_units; st++) {
-        const int uses = (n_units - st + S - 1) / S;
-        ptx::mbar_wait(bar(BAR_EMPTY + st), (uint32_t)((uses - 1) & 1));
-      }
-      for (int a = 0; a < kASlots && a < n_units; a++) {
-        const int uses = (n_units - a + kASlots - 1) / kASlots;
-        ptx::mbar_wait(bar(BAR_EMPTY_A + a * 2 + 0), (uint32_t)((uses - 1) & 1));
-        ptx::mbar_wait(bar(BAR_EMPTY_A + a * 2 + 1), (uint32_t)((uses - 1) & 1));
-      }
-    }
-    FB2_MARK(299);
   } else {
     // ======================================================== dequant + epilogue warps
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int h = warp >> 2;              // which 64-k half of every group this warp owns
     const int nl = q * 32 + lane;         // weight column inside the tile == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t w_off = SC::kXBytes + (uint32_t)h * 4096u + (uint32_t)nl * 16u;   // chunks 2h, 2h+1
-    const uint32_t sz_off = SC::kXBytes + kStageWBytes + (uint32_t)nl * 4u;
+    const uint32_t w_off = SC::kWBase + (uint32_t)h * 4096u + (uint32_t)nl * 16u;    // chunks 2h, 2h+1
+    const uint32_t sz_off = SC::kWBase + kStageWBytes + (uint32_t)nl * 4u;
     const uint32_t a_addr = lane_base + kTmemABase + h * 32;
     const uint32_t bar_full_a = bar(BAR_FULL_A + h), bar_empty_a = bar(BAR_EMPTY_A + h);
-    RingPos rp{0, 0}, ap{0, 0};
+    RingPos wp{0, 0}, ap{0, 0};
     int seg = 0;
     ptx::grid_dependency_wait();          // before the first global write / scratch access
     FB2_TL(2);
@@ -565,11 +556,9 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     Seg sg;
     while (si.next(sg, upt, n_tiles)) {
 #pragma unroll 1
-      for (int n = sg.r1 - sg.r0; n > 0; n--, rp.advance(S), ap.advance(kASlots)) {
-        const uint32_t stage_addr = smem_base + rp.st * SC::kStride;
-        FB2_MARK(300 + n);
-        ptx::mbar_wait(bar(BAR_FULL + rp.st), rp.par);
-        FB2_MARK(350 + n);
+      for (int n = sg.r1 - sg.r0; n > 0; n--, wp.advance(SW), ap.advance(kASlots)) {
+        const uint32_t stage_addr = smem_base + wp.st * kStageBytes;
+        ptx::mbar_wait(bar(BAR_FULL_W + wp.st), wp.par);
         if (tl_first) { FB2_TL(3); tl_first = false; }
         const uint32_t sz = ptx::lds32(stage_addr + sz_off);
         const uint4 w0 = ptx::lds128(stage_addr + w_off);
@@ -590,9 +579,10 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         dequant_word(w1.y, zlo, zhi, s2, r1 + 4);
         dequant_word(w1.z, zlo, zhi, s2, r1 + 8);
         dequant_word(w1.w, zlo, zhi, s2, r1 + 12);
-        // the packed words have been consumed (not merely requested): release the stage
+        // the packed words are in registers (consumed, not merely requested): release the weight
+        // stage to the HBM stream now -- it does not wait for the MMA
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar(BAR_EMPTY + rp.st));
+        if (lane == 0) ptx::mbar_arrive(bar(BAR_EMPTY_W + wp.st));
 
         ptx::mbar_wait(bar_empty_a + ap.st * 16, ap.par ^ 1u);
         ptx::tc_fence_after();
@@ -609,9 +599,9 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       const int r_begin = sg.r0, r_end = sg.r1;                  // [r_begin, r_end) of [0, upt)
       const int blk = sg.blk, tile = sg.tile, tau = sg.blk * n_tiles + sg.tile;
       FB2_TL(4);
-      FB2_MARK(400 + seg);
+
       ptx::mbar_wait(bar(BAR_ACC), seg & 1);
-      FB2_MARK(410 + seg);
+
       FB2_TL(5);
       seg++;
       ptx::tc_fence_after();
@@ -637,7 +627,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       }
       const bool owner = !whole && cta == c_first;
       if (owner) {
-        FB2_MARK(420 + seg);
+
         if (threadIdx.x == 0) {
           const int need = c_last - c_first;
 #ifdef FB2_WAIT_TIMEOUT
@@ -720,23 +710,9 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   }
 
   // -------------------------------------------------------------------------- teardown
-  FB2_MARK(900);
   ptx::tc_fence_before();
   __syncthreads();
-  FB2_MARK(901);
-  if (warp == kWarpMma) {
-    if (ext_tmem == 0xFFFFFFFFu) ptx::tmem_dealloc<kTmemCols>(tmem_base);
-    // the fused MoE kernel runs this body twice in one launch: leave no live mbarrier objects
-    if (kReentrant && lane == 0) {
-      for (int i = 0; i < 2 * kASlots; i++) { ptx::mbar_inval(bar(BAR_FULL_A + i)); ptx::mbar_inval(bar(BAR_EMPTY_A + i)); }
-      ptx::mbar_inval(bar(BAR_ACC));
-      ptx::mbar_inval(bar(BAR_ACC_EMPTY));
-    }
-  } else if (kReentrant && warp == kWarpTma && lane == 0) {
-    for (int i = 0; i < S; i++) { ptx::mbar_inval(bar(BAR_FULL + i)); ptx::mbar_inval(bar(BAR_EMPTY + i)); }
-  }
-  if constexpr (kReentrant) __syncthreads();
-  FB2_MARK(999);
+  if (warp == kWarpMma) ptx::tmem_dealloc<kTmemCols>(tmem_base);
   FB2_TL(7);
 }
 
@@ -752,198 +728,6 @@ tc_gemm_dispatch_kernel(const TcParams p, const __grid_constant__ CUtensorMap xm
                         const __grid_constant__ DispatchTable tbl) {
   ptx::launch_dependents();
   tc_body<NB, false>(p, &tbl, &xmap);
-}
-
-// ------------------------------------------------------------------------------------------
-// Fused MoE FFN for decode-sized batches: ONE persistent launch does
-//   route + align (CTA 0)  | grid barrier |  gate||up grouped GEMM + SiLU*up  | grid barrier |
-//   down grouped GEMM      | grid barrier |  weighted combine
-// i.e. steps 1-6 of moe_forward_bucketed (crates/ferrum-models/src/moe/dispatch.rs:1558-2192), which
-// the reference runs as 8-11 launches.  At batch 1 a layer touches 19.6 MB (3 us of HBM time); five
-// dependent launches cost ten times that, so the launch gaps are what this kernel removes.
-// All CTAs are co-resident (grid = 2 per SM), which is what makes the grid barriers legal.
-struct MoeFusedArgs {
-  const __half *logits;   // [batch, E]
-  int32_t *ids;           // [batch * K]
-  float *wts;             // [batch * K]
-  int32_t *sorted;        // [cap]
-  int32_t *block_ids;     // [cap / block + 1]
-  int32_t *total;         // [1]
-  const __half *down_out; // [pairs, H]   (phase-2 output)
-  __half *out;            // [batch, H]
-  int32_t *sync;          // [2] arrive counter, exit counter (zero between launches)
-  int batch, num_experts, top_k, norm, hidden, block, cap;
-};
-
-__device__ __forceinline__ void grid_barrier(int32_t *arrive, int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(arrive, 1);
-    const long long t0 = clock64();
-    while (ptx::ld_acquire(arrive) < target) {
-      if (clock64() - t0 > 2000000000LL) {                     // ~1 s: a CTA that never became resident
-        printf("fb2: grid barrier timed out (cta %d, target %d)\n", blockIdx.x, target);
-        __trap();
-      }
-    }
-    __threadfence();
-  }
-  // thread 0 left the warp for the spin loop: bar.sync does not reconverge it, and the tcgen05
-  // .sync.aligned instructions that follow need the whole warp executing together
-  __syncwarp();
-  __syncthreads();
-}
-
-// route (router.rs:113-195 semantics, as router_kernel) + align with pair ids, by ONE CTA
-__device__ __forceinline__ void route_align_cta(const MoeFusedArgs &m, float *scratch /* dynamic smem */) {
-  // carved from the (still unused) dynamic shared memory: [warps][E] floats, then three int arrays
-  int *s_ids = reinterpret_cast<int *>(scratch + (size_t)(blockDim.x >> 5) * m.num_experts);
-  int *s_cnt = s_ids + 1024;
-  int *s_off = s_cnt + 1024;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5, nthr = blockDim.x;
-  const int E = m.num_experts, K = m.top_k, pairs = m.batch * K;
-  for (int i = threadIdx.x; i < E; i += nthr) s_cnt[i] = 0;
-  float *probs = scratch + (size_t)warp * E;
-  for (int row = warp; row < m.batch; row += nwarps) {
-    float tmax = -INFINITY;
-    for (int i = lane; i < E; i += 32) {
-      float v = __half2float(m.logits[(size_t)row * E + i]);
-      probs[i] = v;
-      tmax = v > tmax ? v : tmax;
-    }
-    for (int o = 16; o; o >>= 1) {
-      float t = __shfl_xor_sync(0xffffffffu, tmax, o);
-      tmax = t > tmax ? t : tmax;
-    }
-    __syncwarp();
-    for (int i = lane; i < E; i += 32) probs[i] = expf(probs[i] - tmax);
-    __syncwarp();
-    float sum = 0.f;
-    if (lane == 0)
-      for (int i = 0; i < E; i++) sum += probs[i];               // left to right, as router.rs:150-155
-    sum = __shfl_sync(0xffffffffu, sum, 0);
-    const float inv = 1.0f / sum;
-    for (int i = lane; i < E; i += 32) probs[i] *= inv;
-    __syncwarp();
-    float sel_sum = 0.f;
-    for (int k = 0; k < K; k++) {
-      float best = -INFINITY;
-      int best_i = 0x7fffffff;
-      for (int i = lane; i < E; i += 32) {
-        float v = probs[i];
-        if (v > best) { best = v; best_i = i; }
-      }
-      for (int o = 16; o; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-      }
-      if (best_i == 0x7fffffff) best_i = 0;
-      if (lane == 0) {
-        m.ids[(size_t)row * K + k] = best_i;
-        m.wts[(size_t)row * K + k] = best;
-        s_ids[row * K + k] = best_i;
-        probs[best_i] = -INFINITY;
-      }
-      sel_sum += best;
-      __syncwarp();
-    }
-    if (m.norm) {
-      for (int k = lane; k < K; k += 32) {
-        if (sel_sum > 0.f) m.wts[(size_t)row * K + k] *= (1.0f / sel_sum);
-        else m.wts[(size_t)row * K + k] = 1.0f / (float)K;
-      }
-    }
-  }
-  __syncthreads();
-  for (int pidx = threadIdx.x; pidx < pairs; pidx += nthr) atomicAdd(&s_cnt[s_ids[pidx]], 1);    // counts only
-  __syncthreads();
-  if (warp == 0) {
-    // padded offsets: warp-level scan over experts, 32 at a time
-    int carry = 0;
-    for (int e0 = 0; e0 < E; e0 += 32) {
-      const int e = e0 + lane;
-      const int padded = e < E ? ((s_cnt[e] + m.block - 1) / m.block) * m.block : 0;
-      int incl = padded;
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      if (e < E) s_off[e] = carry + incl - padded;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) { s_off[E] = carry; m.total[0] = carry; }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < m.cap; i += nthr) m.sorted[i] = pairs;                             // sentinel
-  __syncthreads();
-  for (int pidx = threadIdx.x; pidx < pairs; pidx += nthr) {
-    const int e = s_ids[pidx];
-    int rank = 0;
-    for (int q = 0; q < pidx; q++) rank += (s_ids[q] == e);       // ascending pair order == the host plan
-    const int slot = s_off[e] + rank;
-    if (slot < m.cap) m.sorted[slot] = pidx;
-  }
-  for (int e = threadIdx.x; e < E; e += nthr)
-    for (int b = s_off[e] / m.block; b < s_off[e + 1] / m.block; b++) m.block_ids[b] = e;
-}
-
-template <int NB, bool kSilu>
-__device__ __noinline__ void tc_body_outlined(const TcParams &p, uint32_t tmem) {
-  tc_body<NB, kSilu, true>(p, nullptr, nullptr, tmem);
-}
-
-__global__ void __launch_bounds__(StageCfg<16>::kBoundThreads, 2)
-moe_ffn_fused_kernel(const TcParams p1, const TcParams p2, const MoeFusedArgs m) {
-  extern __shared__ __align__(1024) uint8_t smem_fused[];
-  ptx::launch_dependents();
-  ptx::grid_dependency_wait();
-  const int G = (int)gridDim.x;
-  FB2_TSTAMP(4);
-  // no static shared memory in this kernel: the dynamic region must start at offset 0 so that the
-  // 1024-byte alignment the UMMA swizzle atoms need holds (tc_body carves it from the same base)
-  uint32_t *s_tmem_fused =
-      reinterpret_cast<uint32_t *>(smem_fused + StageCfg<16>::kStages * StageCfg<16>::kStride + 520);
-  const int warp = threadIdx.x >> 5;
-  if (warp == kWarpMma) ptx::tmem_alloc<256>(ptx::smem_u32(s_tmem_fused));      // once for both GEMM phases
-  if (blockIdx.x == 0) route_align_cta(m, reinterpret_cast<float *>(smem_fused));
-  FB2_TSTAMP(5);
-  ptx::tc_fence_before();
-  grid_barrier(m.sync, G);
-  ptx::tc_fence_after();
-  FB2_TSTAMP(6);
-  const uint32_t tmem = *s_tmem_fused;
-  tc_body_outlined<16, true>(p1, tmem);    // gate||up grouped GEMM, gather + SiLU*up fused
-  FB2_TSTAMP(7);
-  grid_barrier(m.sync, 2 * G);
-  FB2_TSTAMP(8);
-  tc_body_outlined<16, false>(p2, tmem);   // down grouped GEMM
-  FB2_TSTAMP(9);
-  grid_barrier(m.sync, 3 * G);
-  FB2_TSTAMP(10);
-  if (warp == kWarpMma) ptx::tmem_dealloc<256>(tmem);
-  // combine: out[b, h] = sum_k w[b, k] * down[b * K + k, h]  (capabilities.rs:565-600; overwrites out)
-  const int H2 = m.hidden / 2;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < m.batch * H2; idx += G * blockDim.x) {
-    const int b = idx / H2, h2 = idx - b * H2;
-    float a0 = 0.f, a1 = 0.f;
-    for (int k = 0; k < m.top_k; k++) {
-      const float w = m.wts[b * m.top_k + k];
-      const __half2 v = *reinterpret_cast<const __half2 *>(m.down_out + (size_t)(b * m.top_k + k) * m.hidden + h2 * 2);
-      a0 += w * __low2float(v);
-      a1 += w * __high2float(v);
-    }
-    *reinterpret_cast<__half2 *>(m.out + (size_t)b * m.hidden + h2 * 2) =
-        __halves2half2(__float2half_rn(a0), __float2half_rn(a1));
-  }
-  // last CTA out resets the barrier words for the next launch
-  FB2_TSTAMP(11);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int old = atomicAdd(m.sync + 1, 1);
-    if (old == G - 1) { m.sync[0] = 0; m.sync[1] = 0; }
-  }
 }
 
 // ------------------------------------------------------------------------ host planning
@@ -1168,110 +952,6 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
          : nb == 128 ? launch_plain<128, false>(pl, stream, p, xmap) : launch_plain<256, false>(pl, stream, p, xmap);
   }
   if (rc) return rc;
-  count_launch();
-  return FB2_OK;
-}
-
-bool moe_fused_supported(const WeightRef &gu, const WeightRef &dn, size_t batch, size_t top_k) {
-  return tc_supported(gu) && tc_supported(dn) && gu.n % 2 == 0 && (gu.n / 2) % kTileN == 0 && batch >= 1 &&
-         batch <= 32 && batch * top_k <= 1024 && gu.num_experts <= 1024 && gu.perm == nullptr && dn.perm == nullptr;
-}
-
-static int fused_grid(int sm_count) {
-  // One CTA per SM: the occupancy query is conservative for kernels that allocate tensor memory (it
-  // answers 1 although two such CTAs do become co-resident -- scripts/ubench/occ_tmem.cu), and the
-  // in-kernel grid barriers must never wait for a CTA that is not resident.
-  static int per_sm = -1;
-  if (per_sm < 0) {
-    cudaFuncSetAttribute(moe_ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageCfg<16>::kSmemBytes);
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, moe_ffn_fused_kernel, kThreads, StageCfg<16>::kSmemBytes) != cudaSuccess)
-      n = 0;
-    per_sm = n > 2 ? 2 : n;
-    if (const char *e = getenv("FB2_DEBUG_FUSED_PER_SM")) per_sm = atoi(e);   // co-residency experiment
-  }
-  return per_sm * (sm_count > 0 ? sm_count : 148);
-}
-
-void moe_fused_requirements(const WeightRef &gu, const WeightRef &dn, size_t batch, size_t top_k, int sm_count,
-                            size_t *partial_bytes, size_t *counters) {
-  const int grid = fused_grid(sm_count);
-  const size_t pairs = batch * top_k;
-  const size_t nonempty = pairs < (size_t)gu.num_experts ? pairs : (size_t)gu.num_experts;
-  const size_t blocks = (pairs + nonempty * 15) / 16;
-  *partial_bytes = (size_t)grid * 2 * 16 * kTileN * sizeof(float);
-  const size_t t1 = blocks * (size_t)(gu.n / 2 / kTileN), t2 = blocks * (size_t)(dn.n / kTileN);
-  *counters = (t1 > t2 ? t1 : t2) + 2;               // + the two grid-barrier words
-}
-
-int launch_moe_ffn_fused(const WeightRef &gu, const WeightRef &dn, const __half *x, const __half *logits,
-                         __half *out, int32_t *ids, float *wts, int32_t *sorted, int32_t *block_ids,
-                         int32_t *total, __half *act, __half *down_out, size_t batch, size_t top_k, int norm,
-                         size_t cap, const TcScratch &scratch, int sm_count, cudaStream_t stream) {
-  const int grid = fused_grid(sm_count);
-  if (grid < 2) {
-    set_error("fused MoE kernel cannot be made resident");
-    return FB2_ERR_CUDA;
-  }
-  size_t pb, nc;
-  moe_fused_requirements(gu, dn, batch, top_k, sm_count, &pb, &nc);
-  if (pb > scratch.partial_bytes || nc > scratch.num_counters) {
-    set_error("split-K scratch too small for the fused MoE kernel: call fb2_pregrow_scratch");
-    return FB2_ERR_ARG;
-  }
-  const size_t pairs = batch * top_k;
-  const size_t nonempty = pairs < (size_t)gu.num_experts ? pairs : (size_t)gu.num_experts;
-  const int bound = (int)((pairs + nonempty * 15) / 16);
-  auto mk = [&](const WeightRef &w, const __half *xin, __half *yout, int tk, int epilogue) {
-    TcParams p{};
-    p.w = w;
-    p.rm.mode = ROWS_ROUTED;
-    p.rm.sorted_ids = sorted;
-    p.rm.block_experts = block_ids;
-    p.rm.num_post_padded = total;
-    p.rm.block = 16;
-    p.rm.top_k = tk;
-    p.rm.num_valid = (int)pairs;
-    p.rm.max_blocks = bound;
-    p.x = xin;
-    p.y = yout;
-    p.partials = scratch.partials;
-    p.counters = scratch.counters;
-    p.n_tiles = (epilogue ? w.n / 2 : w.n) / kTileN;
-    p.groups = w.k / kGroup;
-    p.tiles_per_expert = w.ld / kTileN;
-    p.ld_out = epilogue ? w.n / 2 : w.n;
-    p.x_tma = 0;
-    return p;
-  };
-  TcParams p1 = mk(gu, x, act, (int)top_k, 1);
-  TcParams p2 = mk(dn, act, down_out, 1, 0);
-#ifdef FB2_TRACE
-  if (const char *tb = getenv("FB2_DEBUG_BUF")) {
-    long long *hp = (long long *)strtoull(tb, nullptr, 10);
-    cudaMemcpyToSymbol(g_trace, &hp, sizeof(hp));
-    fprintf(stderr, "fb2 trace: fused grid %d (sm_count %d)\n", grid, sm_count);
-  }
-#endif
-  MoeFusedArgs m{};
-  m.logits = logits; m.ids = ids; m.wts = wts; m.sorted = sorted; m.block_ids = block_ids; m.total = total;
-  m.down_out = down_out; m.out = out;
-  m.sync = scratch.counters + (nc - 2);
-  m.batch = (int)batch; m.num_experts = gu.num_experts; m.top_k = (int)top_k; m.norm = norm;
-  m.hidden = dn.n; m.block = 16; m.cap = (int)cap;
-  FB2_CUDA_TRY(cudaFuncSetAttribute(moe_ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)StageCfg<16>::kSmemBytes));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = StageCfg<16>::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, moe_ffn_fused_kernel, p1, p2, m));
   count_launch();
   return FB2_OK;
 }

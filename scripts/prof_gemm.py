@@ -33,4 +33,4 @@ for r in range(20):
         lin.forward(x, y, m)
 e1.record()
 torch.cuda.synchronize()
-print(f"K={k} N={n} M={m} kernel={lins[0].kernel_name(m)} avg_us={e0.elapsed_time(e1) * 1e3 / 60:.2f}")
+print(f"K={k} N={n} M={m} kernel={lins[0].kernel_name(m)} avg_us={e0.elapsed_time(e1) * 1e3 / (20 * len(lins)):.2f}")

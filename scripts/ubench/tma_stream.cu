@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(64) stream_kernel(const uint8_t *src, size_t t
 }
 
 int main() {
-  const size_t bytes = 1ull << 30;
+  const size_t bytes = 1ull << 30;   // 16 x 62 MB chain buffers fit
   uint8_t *d; cudaMalloc(&d, bytes); cudaMemset(d, 1, bytes);
   unsigned long long *sink; cudaMalloc(&sink, 8);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -77,6 +77,35 @@ int main() {
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("61MB single launch: %.1f us -> %.0f GB/s\n", ms * 1e3, total_stages * 8704.0 / ms / 1e6);
+  }
+  // chain of back-to-back 61 MB launches over DISTINCT buffers (what a sequence of gate_up GEMMs
+  // streams), timed as a whole: the per-launch cost of a do-nothing streamer
+  {
+    const int chain = 16;
+    const size_t total_stages = 7168;
+    for (int stages : {8, 10}) {
+      for (int rep = 0; rep < 2; rep++) {
+        cudaEventRecord(e0);
+        for (int i = 0; i < chain; i++)
+          stream_kernel<<<296, 64, 8704 * stages + 512>>>(d + (size_t)i * (62 << 20), total_stages, 8704, stages, 1, sink);
+        cudaEventRecord(e1);
+        cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep == 1)
+          printf("chain of %d x 61MB launches, %d stages: %.1f us per launch -> %.0f GB/s\n", chain, stages, ms * 1e3 / chain,
+                 chain * total_stages * 8704.0 / ms / 1e6);
+      }
+    }
+    // same, 148 CTAs (one per SM) with 16 stages, and 592 CTAs with 4
+    for (int rep = 0; rep < 2; rep++) {
+      cudaEventRecord(e0);
+      for (int i = 0; i < chain; i++)
+        stream_kernel<<<148, 64, 8704 * 16 + 512>>>(d + (size_t)i * (62 << 20), total_stages, 8704, 16, 1, sink);
+      cudaEventRecord(e1);
+      cudaDeviceSynchronize();
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      if (rep == 1) printf("chain, 148 CTAs x 16 stages: %.1f us per launch\n", ms * 1e3 / chain);
+    }
   }
   return 0;
 }
