@@ -636,7 +636,8 @@ struct HostArena {
   std::mutex mu;
   uint8_t *h = nullptr, *d = nullptr;
   size_t bytes = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;
 };
 static HostArena g_arena[kMaxDevices];
 
@@ -670,28 +671,71 @@ int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
       if (rc) return rc;
     }
   }
-  if (!A.stream) FB2_CUDA_TRY(cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking));
-  size_t off = 0;
-  for (size_t i = 0; i < n; i++) {
-    memcpy(A.h + off, x_host[i], m * lins[i]->w.k * 2);
-    off += align256(m * lins[i]->w.k * 2);
+  if (!A.stream) {
+    FB2_CUDA_TRY(cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking));
+    FB2_CUDA_TRY(cudaStreamCreateWithFlags(&A.copy_in, cudaStreamNonBlocking));
+    FB2_CUDA_TRY(cudaStreamCreateWithFlags(&A.copy_out, cudaStreamNonBlocking));
   }
-  FB2_CUDA_TRY(cudaMemcpyAsync(A.d, A.h, in_bytes, cudaMemcpyHostToDevice, A.stream));
-  size_t xo = 0, yo = in_bytes;
-  for (size_t i = 0; i < n; i++) {
-    int rc = fb2_gptq_linear_forward(lins[i], A.stream, (const fb2_half *)(A.d + xo),
-                                     (fb2_half *)(A.d + yo), m);
-    if (rc) return rc;
-    xo += align256(m * lins[i]->w.k * 2);
-    yo += align256(m * lins[i]->w.n * 2);
+  // Page-locked caller buffers are DMA'd directly (no staging pass through the arena's pinned half);
+  // pageable ones are staged.  Both directions are decided per call from the first entry.
+  auto is_pinned = [](const void *ptr) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  bool pin_in = true, pin_out = true;
+  for (size_t i = 0; i < n && (pin_in || pin_out); i++) {
+    pin_in = pin_in && is_pinned(x_host[i]);
+    pin_out = pin_out && is_pinned(y_host[i]);
   }
-  FB2_CUDA_TRY(cudaMemcpyAsync(A.h + in_bytes, A.d + in_bytes, out_bytes, cudaMemcpyDeviceToHost, A.stream));
-  FB2_CUDA_TRY(cudaStreamSynchronize(A.stream));
-  yo = in_bytes;
-  for (size_t i = 0; i < n; i++) {
-    memcpy(y_host[i], A.h + yo, m * lins[i]->w.n * 2);
-    yo += align256(m * lins[i]->w.n * 2);
+  // Three streams, chunks of kChunk linears: the H2D copy of chunk c+1 and the D2H copy of chunk
+  // c-1 overlap the GEMMs of chunk c (two copy engines + compute).
+  constexpr size_t kChunk = 16;
+  const size_t chunks = (n + kChunk - 1) / kChunk;
+  if (A.ev_in.size() < chunks) {
+    const size_t old = A.ev_in.size();
+    A.ev_in.resize(chunks);
+    A.ev_done.resize(chunks);
+    for (size_t c = old; c < chunks; c++) {
+      FB2_CUDA_TRY(cudaEventCreateWithFlags(&A.ev_in[c], cudaEventDisableTiming));
+      FB2_CUDA_TRY(cudaEventCreateWithFlags(&A.ev_done[c], cudaEventDisableTiming));
+    }
   }
+  std::vector<size_t> xoff(n), yoff(n);
+  {
+    size_t xo = 0, yo = in_bytes;
+    for (size_t i = 0; i < n; i++) {
+      xoff[i] = xo; yoff[i] = yo;
+      xo += align256(m * lins[i]->w.k * 2);
+      yo += align256(m * lins[i]->w.n * 2);
+    }
+  }
+  for (size_t c = 0; c < chunks; c++) {
+    const size_t i0 = c * kChunk, i1 = std::min(n, i0 + kChunk);
+    for (size_t i = i0; i < i1; i++) {
+      const size_t xb = m * lins[i]->w.k * 2;
+      const void *src = x_host[i];
+      if (!pin_in) { memcpy(A.h + xoff[i], x_host[i], xb); src = A.h + xoff[i]; }
+      FB2_CUDA_TRY(cudaMemcpyAsync(A.d + xoff[i], src, xb, cudaMemcpyHostToDevice, A.copy_in));
+    }
+    FB2_CUDA_TRY(cudaEventRecord(A.ev_in[c], A.copy_in));
+    FB2_CUDA_TRY(cudaStreamWaitEvent(A.stream, A.ev_in[c], 0));
+    for (size_t i = i0; i < i1; i++) {
+      int rc = fb2_gptq_linear_forward(lins[i], A.stream, (const fb2_half *)(A.d + xoff[i]),
+                                       (fb2_half *)(A.d + yoff[i]), m);
+      if (rc) return rc;
+    }
+    FB2_CUDA_TRY(cudaEventRecord(A.ev_done[c], A.stream));
+    FB2_CUDA_TRY(cudaStreamWaitEvent(A.copy_out, A.ev_done[c], 0));
+    for (size_t i = i0; i < i1; i++) {
+      const size_t yb = m * lins[i]->w.n * 2;
+      void *dst = pin_out ? (void *)y_host[i] : (void *)(A.h + yoff[i]);
+      FB2_CUDA_TRY(cudaMemcpyAsync(dst, A.d + yoff[i], yb, cudaMemcpyDeviceToHost, A.copy_out));
+    }
+  }
+  FB2_CUDA_TRY(cudaStreamSynchronize(A.copy_out));
+  if (!pin_out)
+    for (size_t i = 0; i < n; i++) memcpy(y_host[i], A.h + yoff[i], m * lins[i]->w.n * 2);
   return FB2_OK;
 }
 
