@@ -91,6 +91,7 @@ SIGNATURES = {
     "fb2_broadcast_f16": (_i32, [_vp, _vp, _vp, _sz, _i32]),
     "fb2_all_to_all_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fb2_gptq_linear_forward_allreduce": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz]),
+    "fb2_comm_enable_p2p": (_i32, [_vp, _vp, _sz]),
 }
 
 _lib = None

@@ -386,7 +386,8 @@ static int reserve_scratch_for(const WeightRef &w, int device, size_t rows) {
 // then the caller must have called fb2_pregrow_scratch, as the reference requires of
 // pregrow_marlin_gather_scratch, capabilities.rs:205-214).
 static int run_tc(const WeightRef &w_in, const RowMap &rm, const DispatchTable *tbl, const __half *x,
-                  size_t x_rows, __half *y, int epilogue, int device, cudaStream_t stream) {
+                  size_t x_rows, __half *y, int epilogue, int device, cudaStream_t stream,
+                  const PushTargets *push = nullptr) {
   int sms = 0;
   TcScratch sc = current_scratch(device, &sms);
   size_t pb = 0, nc = 0;
@@ -422,7 +423,7 @@ static int run_tc(const WeightRef &w_in, const RowMap &rm, const DispatchTable *
     x = xp;
     w.perm = nullptr;
   }
-  return launch_tc_gemm(w, rm, tbl, x, x_rows, y, epilogue, sc, sms, stream);
+  return launch_tc_gemm(w, rm, tbl, x, x_rows, y, epilogue, sc, sms, stream, push);
 }
 
 // Registry of live weights per device so that fb2_pregrow_scratch can size the pool for
@@ -578,6 +579,29 @@ static WeightRef view_of(const fb2_linear *lin) {
   w.num_experts = 1;
   return w;
 }
+
+}  // extern "C"
+
+namespace fb2 {
+// Row-parallel forward whose epilogue pushes the output tiles to every rank (parallel.cu).
+// *ctas = CTAs that will signal.  UNSUPPORTED when the layer is not on the tensor-core path.
+int forward_linear_push(const fb2_linear_t *lin, cudaStream_t stream, const __half *x, __half *y_unused, size_t m,
+                        const PushTargets *push, uint32_t *ctas) {
+  if (!lin || !x || !push) { set_error("NULL argument"); return FB2_ERR_ARG; }
+  FB2_CUDA_TRY(cudaSetDevice(lin->device));
+  WeightRef w = view_of(lin);
+  if (!tc_supported(w)) { set_error("fused all-reduce needs the tiled weight format"); return FB2_ERR_UNSUPPORTED; }
+  RowMap rm{};
+  rm.mode = ROWS_DENSE;
+  rm.m = (int)m;
+  int sms = 0;
+  current_scratch(lin->device, &sms);
+  *ctas = (uint32_t)tc_grid_size(w, rm, 0, sms);
+  return run_tc(w, rm, nullptr, x, m, y_unused, 0, lin->device, stream, push);
+}
+}  // namespace fb2
+
+extern "C" {
 
 int fb2_gptq_linear_forward(const fb2_linear_t *lin, fb2_stream_t stream, const fb2_half *x,
                             fb2_half *y, size_t m) {

@@ -10,6 +10,8 @@
 
 #include "../../include/fb2_w4a16.h"
 
+struct fb2_linear;   // the C handle (defined in api.cu)
+
 namespace fb2 {
 
 // ----------------------------------------------------------------------------- errors
@@ -132,6 +134,25 @@ int launch_align_block_size(const int32_t *expert_ids, int32_t *sorted_ids, int3
 int launch_moe_combine(const __half *packed_down, const int32_t *pairs_by_token,
                        const float *weights, __half *out, int batch, int hidden, int top_k,
                        cudaStream_t stream);
+// Fused all-reduce of a row-parallel linear (parallel.cu owns the buffers; tc_gemm.cu pushes).
+constexpr int kMaxRanks = 8;
+struct PushTargets {        // kernel parameter of the pushing GEMM; world == 0: plain store to y
+  __half *data[kMaxRanks];           // rank r's receive buffer [2 epochs][world][slot_elems] (peer-mapped)
+  uint32_t *flags[kMaxRanks];        // rank r's arrival counters [2 epochs][world]
+  const uint32_t *epoch;             // this rank's call counter (device memory)
+  size_t slot_elems;
+  int world, rank;
+};
+struct PushExpect { uint32_t ctas[kMaxRanks]; };   // signalling CTAs per source rank
+struct P2pLocal {           // this rank's side of the exchange
+  __half *data; uint32_t *flags, *epoch, *done;
+  size_t slot_elems;
+  int world;
+};
+int forward_linear_push(const ::fb2_linear *lin, cudaStream_t stream, const __half *x, __half *y_unused, size_t m,
+                        const PushTargets *push, uint32_t *ctas);
+int launch_p2p_reduce(const P2pLocal &loc, const PushExpect &expect, __half *y, size_t elems, cudaStream_t stream);
+
 // tc_gemm.cu
 struct TcScratch {
   float *partials;                   // split-K partial sums
@@ -147,7 +168,9 @@ void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int s
 // x_rows: rows of x that may be addressed (bounds of the activation tensor map)
 int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, const __half *x,
                    size_t x_rows, __half *y, int epilogue, const TcScratch &scratch, int sm_count,
-                   cudaStream_t stream);
+                   cudaStream_t stream, const PushTargets *push = nullptr);
+// CTAs the launch above uses (each signals the peers once when it pushes)
+int tc_grid_size(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count);
 const char *tc_kernel_name(const WeightRef &w, size_t m);
 
 }  // namespace fb2

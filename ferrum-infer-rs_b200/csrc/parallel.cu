@@ -149,6 +149,12 @@ using namespace fb2;
 struct fb2_comm {
   NcclComm comm = nullptr;
   int rank = 0, world = 1, device = 0;
+  // one-shot all-reduce over peer memory (fb2_comm_enable_p2p)
+  bool p2p = false;
+  size_t slot_elems = 0;
+  uint8_t *ws = nullptr;                 // this rank's buffer: [data][flags][epoch][done]
+  uint8_t *peer_ws[kMaxRanks] = {};      // IPC mappings (peer_ws[rank] == ws)
+  size_t flags_off = 0, epoch_off = 0, done_off = 0;
 };
 
 extern "C" {
@@ -297,6 +303,13 @@ int fb2_comm_init_rank(const void *unique_id, int rank, int world_size, int devi
 
 void fb2_comm_destroy(fb2_comm_t *comm) {
   if (!comm) return;
+  if (comm->p2p) {
+    cudaSetDevice(comm->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < comm->world; r++)
+      if (r != comm->rank && comm->peer_ws[r]) cudaIpcCloseMemHandle(comm->peer_ws[r]);
+    if (comm->ws) cudaFree(comm->ws);
+  }
   if (comm->comm && nccl().ok) nccl().CommDestroy(comm->comm);
   delete comm;
 }
@@ -358,9 +371,77 @@ int fb2_all_to_all_f16(fb2_comm_t *comm, fb2_stream_t stream, const fb2_half *se
   return FB2_OK;
 }
 
+int fb2_comm_enable_p2p(fb2_comm_t *comm, fb2_stream_t stream, size_t max_elems) {
+  if (!comm) { set_error("comm is NULL"); return FB2_ERR_ARG; }
+  if (comm->p2p) { set_error("peer memory is already enabled on this communicator"); return FB2_ERR_ARG; }
+  if (comm->world > kMaxRanks) { set_error("peer-memory all-reduce supports up to %d ranks", kMaxRanks); return FB2_ERR_UNSUPPORTED; }
+  if (max_elems == 0) { set_error("max_elems is 0"); return FB2_ERR_ARG; }
+  if (comm->world == 1) return FB2_OK;
+  int rc = nccl_ready();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  FB2_CUDA_TRY(cudaSetDevice(comm->device));
+  const size_t slot = (max_elems + 7) / 8 * 8;
+  const size_t data_bytes = 2 * (size_t)comm->world * slot * sizeof(__half);
+  comm->flags_off = (data_bytes + 127) / 128 * 128;
+  comm->epoch_off = comm->flags_off + 2 * (size_t)comm->world * sizeof(uint32_t);
+  comm->done_off = comm->epoch_off + sizeof(uint32_t);
+  const size_t total = comm->done_off + sizeof(uint32_t);
+  FB2_CUDA_TRY(cudaMalloc((void **)&comm->ws, total));
+  FB2_CUDA_TRY(cudaMemset(comm->ws, 0, total));
+  // exchange the IPC handles through the communicator itself (64 bytes per rank)
+  cudaIpcMemHandle_t mine;
+  FB2_CUDA_TRY(cudaIpcGetMemHandle(&mine, comm->ws));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  uint8_t *d_h = nullptr;
+  FB2_CUDA_TRY(cudaMalloc((void **)&d_h, 64 * (size_t)(comm->world + 1)));
+  FB2_CUDA_TRY(cudaMemcpyAsync(d_h, &mine, 64, cudaMemcpyHostToDevice, st));
+  FB2_NCCL_TRY(nccl().AllGather(d_h, d_h + 64, 32 /* halves */, kNcclHalf, comm->comm, st));
+  std::vector<cudaIpcMemHandle_t> all(comm->world);
+  FB2_CUDA_TRY(cudaMemcpyAsync(all.data(), d_h + 64, 64 * (size_t)comm->world, cudaMemcpyDeviceToHost, st));
+  FB2_CUDA_TRY(cudaStreamSynchronize(st));
+  FB2_CUDA_TRY(cudaFree(d_h));
+  for (int r = 0; r < comm->world; r++) {
+    if (r == comm->rank) { comm->peer_ws[r] = comm->ws; continue; }
+    void *ptr = nullptr;
+    FB2_CUDA_TRY(cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess));
+    comm->peer_ws[r] = (uint8_t *)ptr;
+  }
+  // nobody may push before every rank has zeroed its buffer
+  FB2_NCCL_TRY(nccl().AllReduce(comm->ws + comm->done_off, comm->ws + comm->done_off, 2, kNcclHalf, kNcclSum, comm->comm, st));
+  FB2_CUDA_TRY(cudaStreamSynchronize(st));
+  comm->slot_elems = slot;
+  comm->p2p = true;
+  return FB2_OK;
+}
+
 int fb2_gptq_linear_forward_allreduce(const fb2_linear_t *lin, fb2_comm_t *comm, fb2_stream_t stream,
                                       const fb2_half *x, fb2_half *y, size_t m) {
   if (!comm) { set_error("comm is NULL"); return FB2_ERR_ARG; }
+  const size_t elems = m * fb2_gptq_linear_out_features(lin);
+  if (comm->p2p && comm->world > 1 && elems <= comm->slot_elems && elems % 8 == 0 && m > 0) {
+    // fused path: the GEMM epilogue pushes its tiles into every rank's receive slot over NVLink, a
+    // small reduce kernel (PDL-chained) sums the world slots -- no NCCL launch on the critical path
+    PushTargets pt{};
+    for (int r = 0; r < comm->world; r++) {
+      pt.data[r] = (__half *)comm->peer_ws[r];
+      pt.flags[r] = (uint32_t *)(comm->peer_ws[r] + comm->flags_off);
+    }
+    pt.epoch = (const uint32_t *)(comm->ws + comm->epoch_off);
+    pt.slot_elems = comm->slot_elems;
+    pt.world = comm->world;
+    pt.rank = comm->rank;
+    uint32_t ctas = 0;
+    int rc = forward_linear_push(lin, (cudaStream_t)stream, (const __half *)x, (__half *)y, m, &pt, &ctas);
+    if (rc == FB2_OK) {
+      PushExpect ex{};
+      for (int r = 0; r < comm->world; r++) ex.ctas[r] = ctas;   // equal shards: every rank launches the same grid
+      P2pLocal loc{(__half *)comm->ws, (uint32_t *)(comm->ws + comm->flags_off), (uint32_t *)(comm->ws + comm->epoch_off),
+                   (uint32_t *)(comm->ws + comm->done_off), comm->slot_elems, comm->world};
+      return launch_p2p_reduce(loc, ex, (__half *)y, elems, (cudaStream_t)stream);
+    }
+    if (rc != FB2_ERR_UNSUPPORTED) return rc;
+  }
   int rc = fb2_gptq_linear_forward(lin, stream, x, y, m);
   if (rc) return rc;
   return fb2_all_reduce_f16(comm, stream, y, m * fb2_gptq_linear_out_features(lin));

@@ -259,6 +259,11 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 __device__ __forceinline__ void red_release_add(int *addr, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ int ld_acquire(const int *addr) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");

@@ -110,6 +110,7 @@ struct TcParams {
   int ld_out;             // output row stride
   int x_tma;              // activations come through the 2-D tensor map (dense / dispatch rows)
   int whole_tiles;        // dense / dispatch rows: CTA ranges are cut on tile boundaries (host decision)
+  PushTargets push;       // row-parallel linear: output tiles are pushed to every rank's receive slot
 };
 
 // barrier slots (8 bytes each)
@@ -613,6 +614,11 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       const int col = tile * kTileN + nl;
       const float bias = (!kSilu && p.w.bias) ? p.w.bias[col] : 0.0f;
       const bool whole = (r_begin == 0 && r_end == upt);         // this CTA covered the whole tile
+      // Fused all-reduce (row-parallel linear): this rank's finished tiles go straight from the
+      // epilogue into slot [epoch parity][this rank] of EVERY rank's receive buffer (peer memory over
+      // NVLink, IPC-mapped); p2p_reduce_kernel on each rank then sums the world slots.
+      const size_t push_off = p.push.world ? ((size_t)(*(volatile const uint32_t *)p.push.epoch & 1u) * p.push.world +
+                                              p.push.rank) * p.push.slot_elems : 0;
       // A tile cut by CTA range boundaries has contributors c_first .. c_last (consecutive CTAs).
       // c_first -- whose piece of the tile is the LAST segment of its range -- owns the tile: it
       // keeps its own accumulator in registers, waits until the others have published their fp32
@@ -688,7 +694,12 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
             int ar, cr;
             if (!rowmap_resolve(p.rm, tbl, NB, blk, h * HALF + ch * CH + j, ar, cr)) continue;
             const float o = kSilu ? silu_mul(v[0][j], v[NACC - 1][j]) : v[0][j] + bias;
-            p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
+            if (p.push.world == 0) {
+              p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
+            } else {
+              const __half hv = __float2half_rn(o);
+              for (int r = 0; r < p.push.world; r++) p.push.data[r][push_off + (size_t)cr * p.ld_out + col] = hv;
+            }
           }
         } else {
 #pragma unroll
@@ -706,6 +717,16 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         if (threadIdx.x == 0) ptx::red_release_add(p.counters + tau, 1);
         __syncwarp();
       }
+    }
+    if (p.push.world) {
+      // every participating CTA signals every rank once: its pushed tiles are complete
+      ptx::named_bar_sync(1, kDequantWarps * 32);
+      if (threadIdx.x == 0) {
+        const uint32_t par = *(volatile const uint32_t *)p.push.epoch & 1u;
+        __threadfence_system();
+        for (int r = 0; r < p.push.world; r++) atomicAdd_system(p.push.flags[r] + par * p.push.world + p.push.rank, 1u);
+      }
+      __syncwarp();
     }
   }
 
@@ -728,6 +749,54 @@ tc_gemm_dispatch_kernel(const TcParams p, const __grid_constant__ CUtensorMap xm
                         const __grid_constant__ DispatchTable tbl) {
   ptx::launch_dependents();
   tc_body<NB, false>(p, &tbl, &xmap);
+}
+
+// One-shot all-reduce, receive side: wait until every rank's CTAs have signalled this epoch's slot,
+// sum the world slots in rank order (fp32, deterministic), write y.  The last CTA re-arms the flags
+// and advances the epoch (slots and flags are double-buffered by epoch parity, so a peer that is one
+// call ahead never touches what this call still reads).
+__global__ void __launch_bounds__(256) p2p_reduce_kernel(const __half *__restrict__ data, uint32_t *flags,
+                                                         uint32_t *epoch, uint32_t *done, __half *__restrict__ y,
+                                                         size_t elems, size_t slot_elems, int world,
+                                                         const PushExpect expect) {
+  ptx::launch_dependents();
+  ptx::grid_dependency_wait();
+  const uint32_t e = *(volatile uint32_t *)epoch, par = e & 1u;
+  if ((int)threadIdx.x < world) {
+    const uint32_t need = expect.ctas[threadIdx.x];
+    const long long t0 = clock64();
+    while (ptx::ld_acquire_sys(flags + par * world + threadIdx.x) < need) {
+      if (clock64() - t0 > 20000000000LL) { printf("fb2: peer %d never completed its push\n", (int)threadIdx.x); __trap(); }
+    }
+  }
+  __syncthreads();
+  const size_t n8 = elems / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    for (int r = 0; r < world; r++) {
+      const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(data + ((size_t)par * world + r) * slot_elems) + i);
+      const __half2 *hp = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const float2 f = __half22float2(hp[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+    }
+    uint4 o;
+    __half2 *op = reinterpret_cast<__half2 *>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; j++) op[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    reinterpret_cast<uint4 *>(y)[i] = o;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t old = atomicAdd(done, 1u);
+    if (old == gridDim.x - 1) {
+      for (int r = 0; r < world; r++) flags[par * world + r] = 0u;
+      *done = 0u;
+      __threadfence();
+      *(volatile uint32_t *)epoch = e + 1u;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------ host planning
@@ -873,9 +942,37 @@ void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int s
   *counters = pl.counters;
 }
 
+int launch_p2p_reduce(const P2pLocal &loc, const PushExpect &expect, __half *y, size_t elems, cudaStream_t stream) {
+  if (elems % 8 || ((uintptr_t)y % 16)) {
+    set_error("fused all-reduce: output must be 16-byte aligned with a multiple of 8 elements");
+    return FB2_ERR_ARG;
+  }
+  cudaLaunchConfig_t cfg{};
+  const size_t n8 = elems / 8;
+  cfg.gridDim = dim3((unsigned)std::min<size_t>((n8 + 255) / 256, 148));
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, p2p_reduce_kernel, (const __half *)loc.data, loc.flags, loc.epoch, loc.done, y,
+                                  elems, loc.slot_elems, loc.world, expect));
+  count_launch();
+  return FB2_OK;
+}
+
+int tc_grid_size(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count) {
+  int nb, row_blocks;
+  plan_rows(rows, epilogue, nb, row_blocks);
+  if (row_blocks <= 0) return 0;
+  return make_plan(w, rows, epilogue, sm_count).grid;
+}
+
 int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, const __half *x,
                    size_t x_rows, __half *y, int epilogue, const TcScratch &scratch, int sm_count,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const PushTargets *push) {
   if (!tc_supported(w)) {
     set_error("tensor-core path needs the tiled weight format (K,N multiples of 128, group 128)");
     return FB2_ERR_UNSUPPORTED;
@@ -910,6 +1007,7 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   p.tiles_per_expert = w.ld / kTileN;
   p.ld_out = epilogue ? w.n / 2 : w.n;
   p.whole_tiles = pl.whole_tiles;
+  if (push) p.push = *push; else p.push = PushTargets{};
   // Rows that are contiguous in x (dense batches, dispatch entries) come through a 2-D TMA tensor
   // map: one instruction per [NB x 64] box instead of NB*16 cp.async.  Routed rows are gathered.
   CUtensorMap xmap;

@@ -219,6 +219,18 @@ class Comm:
         check(lib().fb2_all_to_all_f16(self._h, self._stream(), send.data_ptr(), offs, cnts, recv.data_ptr(), offs, cnts))
         return recv
 
+    def enable_p2p(self, max_elems: int):
+        """fb2_comm_enable_p2p: afterwards forward_allreduce() fuses the all-reduce of outputs of up to
+        max_elems halves into the GEMM epilogue (peer-memory pushes + one reduce kernel)."""
+        from ._ffi import lib, check
+        check(lib().fb2_comm_enable_p2p(self._h, self._stream(), int(max_elems)))
+
+    def forward_allreduce(self, linear, x, out, m):
+        """fb2_gptq_linear_forward_allreduce on a row-parallel GptqLinear shard."""
+        from ._ffi import lib, check
+        check(lib().fb2_gptq_linear_forward_allreduce(linear._h, self._h, self._stream(), x.data_ptr(), out.data_ptr(), m))
+        return out
+
     def close(self):
         from ._ffi import lib
         if self._h:

@@ -317,6 +317,12 @@ FB2_API int fb2_all_to_all_f16(fb2_comm_t *comm, fb2_stream_t stream, const fb2_
                                const size_t *send_offsets, const size_t *send_counts,
                                fb2_half *recv, const size_t *recv_offsets,
                                const size_t *recv_counts);
+/* Collective over all ranks (synchronises `stream`): allocates this rank's receive buffer for
+ * one-shot all-reduces of up to `max_elems` halves and maps every peer's buffer (CUDA IPC).
+ * Afterwards fb2_gptq_linear_forward_allreduce pushes the GEMM's output tiles to the peers from its
+ * epilogue (NVLink stores) and completes the sum with one small reduce kernel instead of an NCCL
+ * launch, whenever m * out_features <= max_elems.  All ranks must pass the same max_elems. */
+FB2_API int fb2_comm_enable_p2p(fb2_comm_t *comm, fb2_stream_t stream, size_t max_elems);
 FB2_API int fb2_gptq_linear_forward_allreduce(const fb2_linear_t *lin, fb2_comm_t *comm,
                                               fb2_stream_t stream, const fb2_half *x,
                                               fb2_half *y, size_t m);
