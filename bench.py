@@ -213,15 +213,26 @@ def run_gpu(args):
     xs = {m: [torch.randn(m, k, device=dev).clamp_(-1, 1).half() for (k, n) in shapes] for m in DECODE_MS}
     ys = {m: [torch.empty(m, n, device=dev, dtype=torch.float16) for (k, n) in shapes] for m in DECODE_MS}
     row_parallel = [False, True, False, True]
+    comm = None
+    if world > 1:
+        # the library's own communicator; decode-sized row-parallel outputs are all-reduced by the
+        # fused path (GEMM epilogue pushes tiles to the peers over NVLink + one reduce kernel)
+        comm = par.Comm.from_torch_distributed(local)
+        comm.enable_p2p(max(DECODE_MS) * max(n for (k, n) in shapes))
 
-    def step_for(ms):
+    def step_for(ms, fused=True):
         def fn():
             for m in ms:
                 for li in range(layers):
                     for j in range(4):
-                        lins[li][j].forward(xs[m][j], ys[m][j], m)
                         if world > 1 and row_parallel[j]:
-                            par.all_reduce_(ys[m][j])
+                            if fused:
+                                comm.forward_allreduce(lins[li][j], xs[m][j], ys[m][j], m)
+                            else:
+                                lins[li][j].forward(xs[m][j], ys[m][j], m)
+                                par.all_reduce_(ys[m][j])
+                        else:
+                            lins[li][j].forward(xs[m][j], ys[m][j], m)
         return fn
 
     # ------------------------------------------------------------------ headline: decode
@@ -247,6 +258,15 @@ def run_gpu(args):
         series[f"M={m}"] = {"gbs": round(b / (t * 1e-3) / 1e9, 1), "us_per_gemm": round(t * 1e3 / (layers * 4), 2),
                             "frac_hbm": round(b / (t * 1e-3) / 1e9 / pk["hbm_gbs"], 4)}
         del g
+    tp_allreduce = None
+    if world > 1:
+        # same decode step with the row-parallel all-reduces done by NCCL (torch.distributed) instead
+        g = capture(step_for(DECODE_MS, fused=False))
+        t_nccl = time_graph(g, max(3, args.steps // 2), 2, world) / max(3, args.steps // 2)
+        del g
+        tp_allreduce = {"fused_push_ms_per_step": round(ms_step, 4), "nccl_ms_per_step": round(t_nccl, 4),
+                        "speedup": round(t_nccl / ms_step, 3),
+                        "note": "row-parallel o/down: GEMM epilogue pushes tiles to peer memory + reduce kernel, vs GEMM + ncclAllReduce"}
     per_shape = {}
     if world == 1 and not args.quick:
         for j, (name, k, n) in enumerate(LLAMA["linears"]):
@@ -335,7 +355,7 @@ def run_gpu(args):
         e2e = {"value": round(step_bytes / (e_ms * 1e-3) / 1e9, 1), "unit": "GB/s",
                "h2d_bytes_per_step": sum(int(t.nbytes) for m in DECODE_MS for t in hx[m]) * world,
                "d2h_bytes_per_step": sum(int(t.nbytes) for m in DECODE_MS for t in hy[m]) * world,
-               "ms_per_step": round(e_ms, 3), "api": "GptqLinear.forward + all_reduce (per rank)"}
+               "ms_per_step": round(e_ms, 3), "api": "fb2_gptq_linear_forward / fb2_gptq_linear_forward_allreduce (per rank)"}
 
     # ------------------------------------------- Gemma3-27B TP prefill (BASELINE.json configs[4])
     tp_prefill = None
@@ -382,7 +402,8 @@ def run_gpu(args):
                          "kernel": "tc_gemm_kernel (stream-K, tcgen05)", "avg_launch_us": round(avg_launch_us, 3),
                          "alg_bytes_per_launch": int(step_bytes / n_gemms)},
             "cpu_baseline": cpu, "series_decode": series, "per_shape_M1": per_shape, "prefill": prefill,
-            "moe_decode": moe, "tp_prefill_gemma3": tp_prefill, "build_s": round(build_s, 1),
+            "moe_decode": moe, "tp_prefill_gemma3": tp_prefill, "tp_allreduce": tp_allreduce,
+            "build_s": round(build_s, 1),
             "host_cores": os.cpu_count(),
         }
         print(json.dumps(line), flush=True)
