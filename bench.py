@@ -367,7 +367,7 @@ def run_gpu(args):
     # ---------------------------------------------------------------------- MoE series
     moe = None
     if not args.quick and not args.no_moe:
-        moe = run_moe(args, fb2, par, rank, world, local, pk)
+        moe = run_moe(args, fb2, par, rank, world, local, pk, comm)
 
     # ----------------------------------------------------------------------- CPU baseline
     cpu = None
@@ -458,7 +458,7 @@ def run_tp_prefill(args, fb2, par, rank, world, local, pk):
             "parallelism": f"tp{world}", "all_reduce": "nccl (torch.distributed), fp16 [M, hidden], 2 per layer"}
 
 
-def run_moe(args, fb2, par, rank, world, local, pk):
+def run_moe(args, fb2, par, rank, world, local, pk, comm=None):
     """Qwen3-30B-A3B MoE FFN (128 experts, top-8, gate_up 2048->1536, down 768->2048):
     MoE-FFN-only decode tok/s = B / (48 * t_layer).  N > 1: expert parallel."""
     import torch
@@ -485,7 +485,7 @@ def run_moe(args, fb2, par, rank, world, local, pk):
         if world == 1:
             ffns.append(fb2.moe.MoeFfn(gst, dst, K, True, max_batch=max(args.moe_batches)))
         else:
-            ffns.append(par.ExpertParallelFfn(gst, dst, K, True, max(args.moe_batches) // world, E, rank, world))
+            ffns.append(par.ExpertParallelFfn(gst, dst, K, True, max(args.moe_batches) // world, E, rank, world, comm=comm))
     fb2.pregrow_scratch(local, max(args.moe_batches) * K)          # EP: world * (B/world * K) received rows
     out = {}
     for B in args.moe_batches:

@@ -314,8 +314,9 @@ class ExpertParallelFfn:
     ([B_loc, H], router logits [B_loc, E]) and returns their outputs.  Fixed-capacity exchange
     buffers (capacity = B_loc * top_k pairs per peer) keep the whole layer free of host syncs."""
 
-    def __init__(self, gate_up, down, top_k, norm_topk_prob, max_batch, num_experts, rank, world):
+    def __init__(self, gate_up, down, top_k, norm_topk_prob, max_batch, num_experts, rank, world, comm=None):
         import torch
+        self.comm = comm        # fb2 Comm: the f16 exchanges go through fb2_all_to_all_f16 instead of torch
         from . import moe
         self.moe, self.torch = moe, torch
         self.gate_up, self.down = gate_up, down
@@ -355,8 +356,13 @@ class ExpertParallelFfn:
         tok = torch.arange(B * K, device=x.device) // K
         self.send_x[slot] = x[tok]
         if R > 1:
-            dist.all_to_all_single(self.recv_x, self.send_x)
-            dist.all_to_all_single(self.recv_meta, self.send_meta)
+            if self.comm is not None:
+                self.comm.all_to_all_single(self.recv_x, self.send_x)
+                # int32 metadata travels as pairs of halves through the same f16 collective
+                self.comm.all_to_all_single(self.recv_meta.view(torch.float16), self.send_meta.view(torch.float16))
+            else:
+                dist.all_to_all_single(self.recv_x, self.send_x)
+                dist.all_to_all_single(self.recv_meta, self.send_meta)
             rx, rmeta = self.recv_x, self.recv_meta
         else:
             rx, rmeta = self.send_x, self.send_meta
@@ -366,7 +372,10 @@ class ExpertParallelFfn:
         self.gate_up.gemm_phase_vllm(rx, s, b, t, self.act, rows, self.block, 1, silu=True)
         self.down.gemm_phase_vllm(self.act, s, b, t, self.down_out, rows, self.block, 1)
         if R > 1:
-            dist.all_to_all_single(self.ret, self.down_out)
+            if self.comm is not None:
+                self.comm.all_to_all_single(self.ret, self.down_out)
+            else:
+                dist.all_to_all_single(self.ret, self.down_out)
             ret = self.ret
         else:
             ret = self.down_out

@@ -121,6 +121,12 @@ def main():
                                                            act_loc.data_ptr(), y_c.data_ptr(), m))
     torch.cuda.synchronize()
     assert torch.equal(y_c, y_tp), "fb2_gptq_linear_forward_allreduce != TensorParallelLinear + torch all_reduce"
+    # expert-parallel FFN with the dispatch / return all-to-alls through fb2_all_to_all_f16
+    ep_c = par.ExpertParallelFfn(mk(gus[rank * e_loc:(rank + 1) * e_loc], H, 2 * I), mk(dns[rank * e_loc:(rank + 1) * e_loc], I, H),
+                                 K, True, B // world, E, rank, world, comm=comm)
+    y_ep_c = ep_c.forward(torch.from_numpy(xs[sl].astype(np.float16)).to(dev), torch.from_numpy(lg[sl].astype(np.float16)).to(dev))
+    torch.cuda.synchronize()
+    assert torch.equal(y_ep_c, y_ep), "EP through fb2_all_to_all_f16 != EP through torch.distributed"
     # ---------------- fused all-reduce: GEMM epilogue pushes its tiles to the peers (NVLink, IPC-mapped
     # buffers), one reduce kernel completes the sum.  Must match the NCCL path (same fp16 partials; the
     # sum is taken in fp32 in rank order) and be bit-identical under CUDA-graph replay.

@@ -230,3 +230,28 @@ def test_moe_ffn_qwen3_layer_shape(fb2, oracle, cuda):
     for batch in (1, 32):
         st = _ffn_case(fb2, oracle, cuda, 2048, 768, 128, 8, batch, 128, 0x9E3, None)
         assert st["rel"] < 1e-2 and st["nmse"] < 1e-4, (batch, st)
+
+
+@pytest.mark.parametrize("batch,E,top_k,norm", [(1, 60, 4, True), (7, 60, 4, False), (32, 128, 8, True), (32, 8, 1, True),
+                                                 (5, 40, 6, True), (33, 16, 2, True)])
+def test_moe_ffn_odd_router_shapes(fb2, oracle, cuda, batch, E, top_k, norm):
+    """fb2_moe_ffn_forward across router shapes: expert counts that are not multiples of 32, top-1,
+    heavy collisions (32 tokens on 8 experts), and a batch just past the single-launch route+align
+    kernel's limit (33 -> the two-kernel path); against moe_forward_cpu (dispatch.rs:2208-2288)."""
+    torch = cuda
+    hidden, inter, g = 256, 128, 128
+    gus = [oracle.make_synthetic(hidden, 2 * inter, g, 0x3100 + e, f16_scales=True) for e in range(E)]
+    dns = [oracle.make_synthetic(inter, hidden, g, 0x4200 + e, f16_scales=True) for e in range(E)]
+    mk = lambda parts, k, n: fb2.GptqExpertStack.load_gptq_stacked([p.qweight for p in parts], [p.scales for p in parts],
+                                                                   [p.qzeros for p in parts], None, 4, g, k, n)
+    guw = np.stack([oracle.dequant_gptq(p.qweight, p.scales, p.qzeros, None, 4, g, hidden, 2 * inter) for p in gus])
+    dnw = np.stack([oracle.dequant_gptq(p.qweight, p.scales, p.qzeros, None, 4, g, inter, hidden) for p in dns])
+    x = oracle.f16_round(oracle.lcg_f32_array(21, batch * hidden, -1.0, 1.0)).reshape(batch, hidden)
+    lg = oracle.f16_round(oracle.lcg_f32_array(22, batch * E, -2.0, 2.0)).reshape(batch, E)
+    ffn = fb2.moe.MoeFfn(mk(gus, hidden, 2 * inter), mk(dns, inter, hidden), top_k, norm, max_batch=batch)
+    out = ffn.forward(torch.from_numpy(x.astype(np.float16)).cuda(), torch.from_numpy(lg.astype(np.float16)).cuda())
+    torch.cuda.synchronize()
+    ids, w = oracle.route(lg, batch, E, top_k, norm)
+    ref = oracle.moe_forward_cpu(x, batch, hidden, inter, top_k, ids, w, guw, dnw)
+    st = oracle.error_stats(out.float().cpu().numpy(), ref)
+    assert st["rel"] < 1e-2 and st["nmse"] < 1e-5, st
