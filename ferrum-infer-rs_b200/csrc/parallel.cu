@@ -419,7 +419,7 @@ int fb2_gptq_linear_forward_allreduce(const fb2_linear_t *lin, fb2_comm_t *comm,
                                       const fb2_half *x, fb2_half *y, size_t m) {
   if (!comm) { set_error("comm is NULL"); return FB2_ERR_ARG; }
   const size_t elems = m * fb2_gptq_linear_out_features(lin);
-  if (comm->p2p && comm->world > 1 && elems <= comm->slot_elems && elems % 8 == 0 && m > 0) {
+  if (comm->p2p && comm->world > 1 && elems <= comm->slot_elems && elems % 8 == 0 && m > 0 && m <= 64) {
     // fused path: the GEMM epilogue pushes its tiles into every rank's receive slot over NVLink, a
     // small reduce kernel (PDL-chained) sums the world slots -- no NCCL launch on the critical path
     PushTargets pt{};

@@ -273,7 +273,11 @@ __device__ __forceinline__ long long fb2_gtime() { long long t; asm volatile("mo
 #define FB2_TLV(slot, v) do { } while (0)
 #endif
 
-template <int NB, bool kSilu>
+// kPush instantiations (row-parallel decode GEMMs with the fused all-reduce) are separate kernels: the
+// push branches in the epilogue cost the prefill variant 13 % when they were a run-time test.
+#define push_world(p) (kPush ? (p).push.world : 0)
+
+template <int NB, bool kSilu, bool kPush = false>
 __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *tbl, const CUtensorMap *xmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SC = StageCfg<NB>;
@@ -617,7 +621,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       // Fused all-reduce (row-parallel linear): this rank's finished tiles go straight from the
       // epilogue into slot [epoch parity][this rank] of EVERY rank's receive buffer (peer memory over
       // NVLink, IPC-mapped); p2p_reduce_kernel on each rank then sums the world slots.
-      const size_t push_off = p.push.world ? ((size_t)(*(volatile const uint32_t *)p.push.epoch & 1u) * p.push.world +
+      const size_t push_off = push_world(p) ? ((size_t)(*(volatile const uint32_t *)p.push.epoch & 1u) * p.push.world +
                                               p.push.rank) * p.push.slot_elems : 0;
       // A tile cut by CTA range boundaries has contributors c_first .. c_last (consecutive CTAs).
       // c_first -- whose piece of the tile is the LAST segment of its range -- owns the tile: it
@@ -694,11 +698,11 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
             int ar, cr;
             if (!rowmap_resolve(p.rm, tbl, NB, blk, h * HALF + ch * CH + j, ar, cr)) continue;
             const float o = kSilu ? silu_mul(v[0][j], v[NACC - 1][j]) : v[0][j] + bias;
-            if (p.push.world == 0) {
+            if (push_world(p) == 0) {
               p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
             } else {
               const __half hv = __float2half_rn(o);
-              for (int r = 0; r < p.push.world; r++) p.push.data[r][push_off + (size_t)cr * p.ld_out + col] = hv;
+              for (int r = 0; r < push_world(p); r++) p.push.data[r][push_off + (size_t)cr * p.ld_out + col] = hv;
             }
           }
         } else {
@@ -718,7 +722,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         __syncwarp();
       }
     }
-    if (p.push.world) {
+    if (push_world(p)) {
       // every participating CTA signals every rank once: its pushed tiles are complete
       ptx::named_bar_sync(1, kDequantWarps * 32);
       if (threadIdx.x == 0) {
@@ -737,11 +741,11 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   FB2_TL(7);
 }
 
-template <int NB, bool kSilu>
+template <int NB, bool kSilu, bool kPush = false>
 __global__ void __launch_bounds__(StageCfg<NB>::kBoundThreads, StageCfg<NB>::kCtasPerSm)
 tc_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
   ptx::launch_dependents();
-  tc_body<NB, kSilu>(p, nullptr, &xmap);
+  tc_body<NB, kSilu, kPush>(p, nullptr, &xmap);
 }
 template <int NB>
 __global__ void __launch_bounds__(StageCfg<NB>::kBoundThreads, StageCfg<NB>::kCtasPerSm)
@@ -842,6 +846,17 @@ TcPlan make_plan(const WeightRef &w, const RowMap &rows, int epilogue, int sm_co
   long long g = pl.whole_tiles ? units / upt : units / 2;         // whole tiles | >= 2 units per CTA
   if (g < 1) g = 1;
   pl.grid = (int)(g < slots ? g : slots);
+  // Few tiles (decode qkv / o / down: 32-48 of them): give every tile the same whole number s of
+  // CTAs.  With G = tiles * s the ranges c*T/G fall on tile boundaries, so no CTA straddles two tiles
+  // (a straddling CTA pays a mid-stream epilogue AND owns the next tile's fix-up: it was the
+  // straggler of these launches in the in-kernel timeline).
+  static const bool no_align = [] { const char *e = getenv("FB2_DEBUG_NO_TILE_ALIGN"); return e && e[0] == '1'; }();
+  const long long nt = units / upt;
+  if (!no_align && !pl.whole_tiles && rows.mode != ROWS_ROUTED && nt > 0 && nt * 2 <= slots) {
+    long long s = slots / nt;
+    if (s > upt / 2) s = upt / 2;                                   // >= 2 units per CTA
+    if (s >= 1) pl.grid = (int)(nt * s);
+  }
   pl.partial_floats = (size_t)pl.grid * pl.nacc * pl.nb * kTileN;
   pl.counters = (size_t)pl.row_blocks * pl.n_tiles;
   pl.smem = pl.nb == 16 ? smem_of<16>() : pl.nb == 32 ? smem_of<32>() : pl.nb == 64 ? smem_of<64>()
@@ -898,13 +913,13 @@ void launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, const TcPlan
   cfg.numAttrs = 1;
 }
 
-template <int NB, bool kSilu>
+template <int NB, bool kSilu, bool kPush = false>
 int launch_plain(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
-  FB2_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<NB, kSilu>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  FB2_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<NB, kSilu, kPush>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   launch_cfg(cfg, attr, pl, stream);
-  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NB, kSilu>, p, xmap));
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NB, kSilu, kPush>, p, xmap));
   return FB2_OK;
 }
 template <int NB>
@@ -1037,7 +1052,14 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   }
 #endif
   int rc;
-  if (tbl) {
+  if (push && push->world) {
+    if (tbl || epilogue || nb > 64) {
+      set_error("fused all-reduce: decode-sized dense launches only (<= 64 rows per block)");
+      return FB2_ERR_UNSUPPORTED;
+    }
+    rc = nb == 16 ? launch_plain<16, false, true>(pl, stream, p, xmap)
+         : nb == 32 ? launch_plain<32, false, true>(pl, stream, p, xmap) : launch_plain<64, false, true>(pl, stream, p, xmap);
+  } else if (tbl) {
     rc = nb == 16 ? launch_dispatch<16>(pl, stream, p, xmap, *tbl)
          : nb == 32 ? launch_dispatch<32>(pl, stream, p, xmap, *tbl) : launch_dispatch<64>(pl, stream, p, xmap, *tbl);
   } else if (epilogue) {
