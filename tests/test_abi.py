@@ -99,3 +99,29 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), f
                 assert "liboracle" not in text and "oracle.c" not in text, f
+
+
+def test_collective_argument_errors(fb2):
+    """fb2_comm_* / fb2_all_* validate their handles before touching NCCL or a device."""
+    lib = fb2.lib()
+    ffi = importlib.import_module("ferrum-infer-rs_b200._ffi")
+    assert lib.fb2_comm_world_size(None) == 1 and lib.fb2_comm_rank(None) == 0      # "no communicator" == 1 rank
+    for rc in (lib.fb2_all_reduce_f16(None, None, None, 16), lib.fb2_all_gather_f16(None, None, None, None, 16),
+               lib.fb2_broadcast_f16(None, None, None, 16, 0), lib.fb2_comm_enable_p2p(None, None, 1024),
+               lib.fb2_all_to_all_f16(None, None, None, None, None, None, None, None),
+               lib.fb2_gptq_linear_forward_allreduce(None, None, None, None, None, 1)):
+        assert rc == -5                                                              # FB2_ERR_ARG
+        assert b"comm" in lib.fb2_last_error()
+    out = C.c_void_p()
+    assert lib.fb2_comm_init_rank(None, 0, 1, 0, C.byref(out)) == -5
+    buf = C.create_string_buffer(128)
+    assert lib.fb2_comm_init_rank(buf, 3, 2, 0, C.byref(out)) == -5                  # rank outside the world
+    assert lib.fb2_comm_get_unique_id(None) == -5
+    lib.fb2_comm_destroy(None)                                                       # no-op
+    k_l, n_l = C.c_size_t(), C.c_size_t()
+    assert lib.fb2_gptq_shard_dims(4096, 4096, 128, 1, 0, 8, None, 0, C.byref(k_l), C.byref(n_l)) == 0
+    assert (k_l.value, n_l.value) == (512, 4096)                                     # o_proj at tp=8: 4 groups
+    seg = (C.c_size_t * 3)(4096, 1024, 1024)
+    assert lib.fb2_gptq_shard_dims(4096, 6144, 128, 0, 3, 8, seg, 3, C.byref(k_l), C.byref(n_l)) == 0
+    assert (k_l.value, n_l.value) == (4096, 768)                                     # qkv at tp=8
+    assert lib.fb2_gptq_shard_dims(4096, 4096, 128, 7, 0, 2, None, 0, None, None) == -5
