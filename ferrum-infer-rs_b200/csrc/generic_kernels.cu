@@ -329,7 +329,8 @@ int launch_permute_cols(const __half *x, const int32_t *perm, __half *xp, int m,
   cfg.numAttrs = 1;
   const size_t row_bytes = (size_t)k * sizeof(__half);
   const bool aligned = k % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)xp % 16) == 0 && ((uintptr_t)perm % 16) == 0;
-  if (m >= 16 && aligned && row_bytes <= 48 * 1024) {
+  static const int rows_min = [] { const char *e = getenv("FB2_DEBUG_PERMUTE_ROWS_MIN"); return e ? atoi(e) : 64; }();
+  if (m >= rows_min && aligned && row_bytes <= 48 * 1024) {
     // batched rows: one CTA per row through shared memory
     cfg.gridDim = dim3(m < 1184 ? m : 1184);
     cfg.dynamicSmemBytes = row_bytes;
