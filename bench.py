@@ -485,7 +485,8 @@ def run_moe(args, fb2, par, rank, world, local, pk, comm=None):
         if world == 1:
             ffns.append(fb2.moe.MoeFfn(gst, dst, K, True, max_batch=max(args.moe_batches)))
         else:
-            ffns.append(par.ExpertParallelFfn(gst, dst, K, True, max(args.moe_batches) // world, E, rank, world, comm=comm))
+            ffns.append(par.ExpertParallelFfn(gst, dst, K, True, max(args.moe_batches) // world, E, rank, world,
+                                              comm=comm).enable_native())
     fb2.pregrow_scratch(local, max(args.moe_batches) * K)          # EP: world * (B/world * K) received rows
     out = {}
     for B in args.moe_batches:

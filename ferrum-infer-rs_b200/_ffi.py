@@ -92,6 +92,8 @@ SIGNATURES = {
     "fb2_all_to_all_f16": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fb2_gptq_linear_forward_allreduce": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz]),
     "fb2_comm_enable_p2p": (_i32, [_vp, _vp, _sz]),
+    "fb2_moe_ep_workspace_bytes": (_sz, [_vp, _vp, _sz, _sz, _i32]),
+    "fb2_moe_ep_ffn_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _i32, _vp, _sz]),
 }
 
 _lib = None

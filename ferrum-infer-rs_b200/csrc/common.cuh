@@ -125,6 +125,12 @@ bool route_align_small_supported(int batch, int num_experts, int top_k);
 int launch_route_align_small(const __half *logits, int32_t *ids, float *wts, int32_t *sorted_ids,
                              int32_t *block_ids, int32_t *total_post_pad, int batch, int num_experts, int top_k,
                              int norm, int block_size, int sorted_max, cudaStream_t stream);
+// expert parallelism, sender side: routing + dispatch plan in one launch; row scatter into the send buffer
+bool ep_route_plan_supported(int batch, int num_experts, int top_k, int world);
+int launch_ep_route_plan(const __half *logits, int32_t *ids, float *wts, int32_t *slot_of_pair, int32_t *send_meta,
+                         int batch, int num_experts, int top_k, int norm, int world, int cap, cudaStream_t stream);
+int launch_ep_scatter_rows(const __half *x, const int32_t *slot_of_pair, __half *send_x, int pairs, int hidden, int top_k,
+                           cudaStream_t stream);
 int launch_build_pairs(const int32_t *expert_ids, int32_t *pairs_by_token,
                        int32_t *packed_token_idx, int32_t *expert_offsets, int pairs,
                        int num_experts, int top_k, cudaStream_t stream);

@@ -320,6 +320,103 @@ route_align_small_kernel(const __half *__restrict__ logits, int32_t *__restrict_
   }
 }
 
+// Expert parallelism, sender side: route this rank's tokens and plan the dispatch in ONE single-CTA
+// launch.  Pair p = (token, k) goes to rank dest = id / e_loc, into slot (ordered count of earlier
+// pairs with the same destination) of the fixed-capacity send buffer [world][cap]; send_meta holds
+// the expert id local to the destination (-1 = empty slot).  slot_of_pair feeds the combine.
+__global__ void __launch_bounds__(kRouteAlignThreads)
+ep_route_plan_kernel(const __half *__restrict__ logits, int32_t *__restrict__ out_ids, float *__restrict__ out_w,
+                     int32_t *__restrict__ slot_of_pair, int32_t *__restrict__ send_meta, int batch, int num_experts,
+                     int top_k, int norm, int world, int cap) {
+  extern __shared__ float s_probs[];                  // [32 warps][num_experts]
+  __shared__ int s_dest_id[kRouteAlignThreads];       // expert id of pair p
+  __shared__ int warp_sums[64];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kRouteAlignThreads / 32;
+  const int pairs = batch * top_k, e_loc = num_experts / world;
+  for (int i = threadIdx.x; i < world * cap; i += kRouteAlignThreads) send_meta[i] = -1;
+  for (int row = warp; row < batch; row += nwarps) {
+    float *probs = s_probs + (size_t)warp * num_experts;
+    float tmax = -INFINITY;
+    for (int i = lane; i < num_experts; i += 32) {
+      float v = __half2float(logits[(size_t)row * num_experts + i]);
+      probs[i] = v;
+      tmax = v > tmax ? v : tmax;
+    }
+    for (int o = 16; o; o >>= 1) {
+      float t = __shfl_xor_sync(0xffffffffu, tmax, o);
+      tmax = t > tmax ? t : tmax;
+    }
+    __syncwarp();
+    for (int i = lane; i < num_experts; i += 32) probs[i] = expf(probs[i] - tmax);
+    __syncwarp();
+    float sum = 0.f;
+    if (lane == 0)
+      for (int i = 0; i < num_experts; i++) sum += probs[i];   // left to right, as router.rs:150-155
+    sum = __shfl_sync(0xffffffffu, sum, 0);
+    const float inv = 1.0f / sum;
+    for (int i = lane; i < num_experts; i += 32) probs[i] *= inv;
+    __syncwarp();
+    float sel_sum = 0.f;
+    for (int k = 0; k < top_k; k++) {
+      float best = -INFINITY;
+      int best_i = 0x7fffffff;
+      for (int i = lane; i < num_experts; i += 32) {
+        float v = probs[i];
+        if (v > best) { best = v; best_i = i; }
+      }
+      for (int o = 16; o; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+      }
+      if (best_i == 0x7fffffff) best_i = 0;
+      if (lane == 0) {
+        out_ids[(size_t)row * top_k + k] = best_i;
+        out_w[(size_t)row * top_k + k] = best;
+        s_dest_id[row * top_k + k] = best_i;
+        probs[best_i] = -INFINITY;
+      }
+      sel_sum += best;
+      __syncwarp();
+    }
+    if (norm) {
+      for (int k = lane; k < top_k; k += 32) {
+        if (sel_sum > 0.f) out_w[(size_t)row * top_k + k] *= (1.0f / sel_sum);
+        else out_w[(size_t)row * top_k + k] = 1.0f / (float)top_k;
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // ordered slot of every pair inside its destination's run: one block scan per destination rank
+  const int pidx = threadIdx.x;
+  const int my_id = pidx < pairs ? s_dest_id[pidx] : -1;
+  const int my_dest = my_id >= 0 ? my_id / e_loc : -1;
+  for (int r = 0; r < world; r++) {
+    int total;
+    const int rank_in = block_exclusive_scan(my_dest == r ? 1 : 0, warp_sums, total);
+    if (my_dest == r) {
+      const int slot = r * cap + rank_in;                        // rank_in < cap: cap = batch * top_k
+      slot_of_pair[pidx] = slot;
+      send_meta[slot] = my_id - r * e_loc;
+    }
+  }
+}
+
+// One CTA per pair: x[pair / top_k] -> send_x[slot_of_pair[pair]] (16-byte vectors).
+__global__ void __launch_bounds__(128)
+ep_scatter_rows_kernel(const __half *__restrict__ x, const int32_t *__restrict__ slot_of_pair,
+                       __half *__restrict__ send_x, int hidden, int top_k) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int p = blockIdx.x;
+  const uint4 *src = reinterpret_cast<const uint4 *>(x + (size_t)(p / top_k) * hidden);
+  uint4 *dst = reinterpret_cast<uint4 *>(send_x + (size_t)slot_of_pair[p] * hidden);
+  for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = src[i];
+}
+
 template <bool kPairs>
 __global__ void combine_kernel(const __half *__restrict__ rows, const int32_t *__restrict__ pairs_by_token,
                                const float *__restrict__ weights, __half *__restrict__ out,
@@ -383,6 +480,24 @@ int launch_route_align_small(const __half *logits, int32_t *ids, float *wts, int
     FB2_CUDA_TRY(cudaFuncSetAttribute(route_align_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return launch_pdl(route_align_small_kernel, dim3(1), dim3(kRouteAlignThreads), smem, stream, logits, ids, wts,
                     sorted_ids, block_ids, total_post_pad, batch, num_experts, top_k, norm, block_size, sorted_max);
+}
+
+bool ep_route_plan_supported(int batch, int num_experts, int top_k, int world) {
+  return batch >= 1 && batch * top_k <= kRouteAlignThreads && num_experts <= 256 && world >= 1 &&
+         num_experts % world == 0 && top_k <= num_experts;
+}
+
+int launch_ep_route_plan(const __half *logits, int32_t *ids, float *wts, int32_t *slot_of_pair, int32_t *send_meta,
+                         int batch, int num_experts, int top_k, int norm, int world, int cap, cudaStream_t stream) {
+  const size_t smem = (size_t)32 * num_experts * sizeof(float);
+  return launch_pdl(ep_route_plan_kernel, dim3(1), dim3(kRouteAlignThreads), smem, stream, logits, ids, wts, slot_of_pair,
+                    send_meta, batch, num_experts, top_k, norm, world, cap);
+}
+
+int launch_ep_scatter_rows(const __half *x, const int32_t *slot_of_pair, __half *send_x, int pairs, int hidden, int top_k,
+                           cudaStream_t stream) {
+  if (pairs <= 0) return FB2_OK;
+  return launch_pdl(ep_scatter_rows_kernel, dim3(pairs), dim3(128), 0, stream, x, slot_of_pair, send_x, hidden, top_k);
 }
 
 int launch_build_pairs(const int32_t *expert_ids, int32_t *pairs_by_token,

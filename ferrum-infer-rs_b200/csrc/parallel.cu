@@ -371,6 +371,114 @@ int fb2_all_to_all_f16(fb2_comm_t *comm, fb2_stream_t stream, const fb2_half *se
   return FB2_OK;
 }
 
+// ----------------------------------------------------------------- expert-parallel MoE FFN
+namespace {
+struct EpLayout {
+  size_t ids, wts, slot, send_meta, recv_meta, sorted, block_ids, total, send_x, recv_x, act, down_out, ret, bytes;
+  size_t cap, rows, sorted_cap;
+};
+EpLayout ep_layout(size_t batch_loc, size_t top_k, size_t world, size_t e_loc, size_t hidden, size_t inter) {
+  EpLayout L{};
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  L.cap = batch_loc * top_k;
+  L.rows = world * L.cap;
+  L.sorted_cap = L.rows + e_loc * 16;
+  size_t o = 0;
+  L.ids = o; o += al(L.cap * 4);
+  L.wts = o; o += al(L.cap * 4);
+  L.slot = o; o += al(L.cap * 4);
+  L.send_meta = o; o += al(L.rows * 4);
+  L.recv_meta = o; o += al(L.rows * 4);
+  L.sorted = o; o += al(L.sorted_cap * 4);
+  L.block_ids = o; o += al((L.sorted_cap / 16 + 1) * 4);
+  L.total = o; o += 256;
+  L.send_x = o; o += al(L.rows * hidden * 2);
+  L.recv_x = o; o += al(L.rows * hidden * 2);
+  L.act = o; o += al(L.rows * inter * 2);
+  L.down_out = o; o += al(L.rows * hidden * 2);
+  L.ret = o; o += al(L.rows * hidden * 2);
+  L.bytes = o;
+  return L;
+}
+}  // namespace
+
+size_t fb2_moe_ep_workspace_bytes(const fb2_stack_t *gate_up, const fb2_stack_t *down, size_t max_batch_local,
+                                  size_t top_k, int world_size) {
+  if (!gate_up || !down || world_size < 1) return 0;
+  return ep_layout(max_batch_local, top_k, (size_t)world_size, fb2_gptq_stack_num_experts(gate_up),
+                   fb2_gptq_stack_k(gate_up), fb2_gptq_stack_n_per_expert(gate_up) / 2).bytes;
+}
+
+int fb2_moe_ep_ffn_forward(const fb2_stack_t *gate_up, const fb2_stack_t *down, fb2_comm_t *comm, fb2_stream_t stream,
+                           const fb2_half *x, const fb2_half *router_logits, fb2_half *out, size_t batch_local,
+                           size_t top_k, int norm_topk_prob, void *workspace, size_t workspace_bytes) {
+  if (!gate_up || !down || !comm || !workspace) { set_error("NULL argument (stacks, comm, workspace)"); return FB2_ERR_ARG; }
+  if (batch_local == 0) return FB2_OK;
+  if (!x || !router_logits || !out) { set_error("x / router_logits / out is NULL"); return FB2_ERR_ARG; }
+  const size_t world = (size_t)comm->world, e_loc = fb2_gptq_stack_num_experts(gate_up);
+  const size_t hidden = fb2_gptq_stack_k(gate_up), inter = fb2_gptq_stack_n_per_expert(gate_up) / 2;
+  if (fb2_gptq_stack_num_experts(down) != e_loc || fb2_gptq_stack_k(down) != inter || fb2_gptq_stack_n_per_expert(down) != hidden) {
+    set_error("expert-parallel FFN: gate_up [%zu -> 2*%zu] and down stacks do not match", hidden, inter);
+    return FB2_ERR_SHAPE;
+  }
+  const size_t E = e_loc * world;
+  if (!ep_route_plan_supported((int)batch_local, (int)E, (int)top_k, (int)world) || hidden % 8) {
+    set_error("expert-parallel FFN: needs batch_local * top_k <= 1024, <= 256 experts, hidden %% 8 == 0");
+    return FB2_ERR_UNSUPPORTED;
+  }
+  const EpLayout L = ep_layout(batch_local, top_k, world, e_loc, hidden, inter);
+  if (workspace_bytes < L.bytes) { set_error("workspace too small: %zu < %zu bytes", workspace_bytes, L.bytes); return FB2_ERR_ARG; }
+  FB2_CUDA_TRY(cudaSetDevice(comm->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t *ws = (uint8_t *)workspace;
+  int32_t *ids = (int32_t *)(ws + L.ids), *slot = (int32_t *)(ws + L.slot), *send_meta = (int32_t *)(ws + L.send_meta);
+  int32_t *recv_meta = (int32_t *)(ws + L.recv_meta), *sorted = (int32_t *)(ws + L.sorted);
+  int32_t *block_ids = (int32_t *)(ws + L.block_ids), *total = (int32_t *)(ws + L.total);
+  float *wts = (float *)(ws + L.wts);
+  __half *send_x = (__half *)(ws + L.send_x), *recv_x = (__half *)(ws + L.recv_x), *act = (__half *)(ws + L.act);
+  __half *down_out = (__half *)(ws + L.down_out), *ret = (__half *)(ws + L.ret);
+  int rc;
+  // 1. route this rank's tokens + dispatch plan (one launch), 2. rows into the send buffer
+  if ((rc = launch_ep_route_plan((const __half *)router_logits, ids, wts, slot, send_meta, (int)batch_local, (int)E,
+                                 (int)top_k, norm_topk_prob, (int)world, (int)L.cap, st))) return rc;
+  if ((rc = launch_ep_scatter_rows((const __half *)x, slot, send_x, (int)L.cap, (int)hidden, (int)top_k, st))) return rc;
+  // 3. dispatch: rows and their expert ids to the expert owners -- ONE grouped all-to-all
+  const size_t xb = L.cap * hidden, mb = L.cap * 2;              // elements (halves) per peer
+  if (world > 1) {
+    rc = nccl_ready();
+    if (rc) return rc;
+    FB2_NCCL_TRY(nccl().GroupStart());
+    for (size_t peer = 0; peer < world; peer++) {
+      FB2_NCCL_TRY(nccl().Send(send_x + peer * xb, xb, kNcclHalf, (int)peer, comm->comm, st));
+      FB2_NCCL_TRY(nccl().Recv(recv_x + peer * xb, xb, kNcclHalf, (int)peer, comm->comm, st));
+      FB2_NCCL_TRY(nccl().Send((const __half *)send_meta + peer * mb, mb, kNcclHalf, (int)peer, comm->comm, st));
+      FB2_NCCL_TRY(nccl().Recv((__half *)recv_meta + peer * mb, mb, kNcclHalf, (int)peer, comm->comm, st));
+    }
+    FB2_NCCL_TRY(nccl().GroupEnd());
+  } else {
+    recv_x = send_x;
+    recv_meta = send_meta;
+  }
+  // 4. local grouped GEMMs over the received rows (row id == position in the receive buffer, top_k = 1)
+  if ((rc = fb2_moe_align_block_size(stream, recv_meta, sorted, block_ids, total, L.rows, e_loc, 16, L.sorted_cap, 1))) return rc;
+  if ((rc = fb2_gptq_stack_gemm_routed_silu(gate_up, stream, (const fb2_half *)recv_x, sorted, block_ids, total,
+                                            (fb2_half *)act, L.rows, 16, 1, L.sorted_cap))) return rc;
+  if ((rc = fb2_gptq_stack_gemm_routed(down, stream, (const fb2_half *)act, sorted, block_ids, total,
+                                       (fb2_half *)down_out, L.rows, 16, 1, L.sorted_cap))) return rc;
+  // 5. return to the token owners, 6. weighted combine over this rank's tokens
+  if (world > 1) {
+    FB2_NCCL_TRY(nccl().GroupStart());
+    for (size_t peer = 0; peer < world; peer++) {
+      FB2_NCCL_TRY(nccl().Send(down_out + peer * xb, xb, kNcclHalf, (int)peer, comm->comm, st));
+      FB2_NCCL_TRY(nccl().Recv(ret + peer * xb, xb, kNcclHalf, (int)peer, comm->comm, st));
+    }
+    FB2_NCCL_TRY(nccl().GroupEnd());
+  } else {
+    ret = down_out;
+  }
+  return fb2_moe_combine(stream, (const fb2_half *)ret, slot, wts, out, batch_local, hidden, top_k);
+}
+
 int fb2_comm_enable_p2p(fb2_comm_t *comm, fb2_stream_t stream, size_t max_elems) {
   if (!comm) { set_error("comm is NULL"); return FB2_ERR_ARG; }
   if (comm->p2p) { set_error("peer memory is already enabled on this communicator"); return FB2_ERR_ARG; }

@@ -317,6 +317,7 @@ class ExpertParallelFfn:
     def __init__(self, gate_up, down, top_k, norm_topk_prob, max_batch, num_experts, rank, world, comm=None):
         import torch
         self.comm = comm        # fb2 Comm: the f16 exchanges go through fb2_all_to_all_f16 instead of torch
+        self.native = False     # set by enable_native(): run the layer through fb2_moe_ep_ffn_forward
         from . import moe
         self.moe, self.torch = moe, torch
         self.gate_up, self.down = gate_up, down
@@ -340,6 +341,17 @@ class ExpertParallelFfn:
 
     def forward(self, x, router_logits, out=None):
         torch, moe = self.torch, self.moe
+        if self.comm is not None and self.native:
+            # fb2_moe_ep_ffn_forward: the whole layer inside the library (8 launches incl. 2 all-to-alls)
+            from ._ffi import lib, check
+            B = x.shape[0]
+            if out is None:
+                out = torch.empty((B, self.hidden), dtype=torch.float16, device=x.device)
+            check(lib().fb2_moe_ep_ffn_forward(self.gate_up._h, self.down._h, self.comm._h,
+                                               torch.cuda.current_stream().cuda_stream, x.data_ptr(),
+                                               router_logits.data_ptr(), out.data_ptr(), B, self.top_k,
+                                               1 if self.norm else 0, self.workspace.data_ptr(), self.workspace.numel()))
+            return out
         import torch.distributed as dist
         B = x.shape[0]
         K, R, C = self.top_k, self.world, self.cap
@@ -382,4 +394,14 @@ class ExpertParallelFfn:
         moe.moe_combine(ret, slot.to(torch.int32).contiguous(), w.reshape(-1).contiguous(), out, B, self.hidden, K)
         return out
 
+    def enable_native(self):
+        """Run the layer through fb2_moe_ep_ffn_forward (needs `comm`)."""
+        from ._ffi import lib
+        assert self.comm is not None
+        n = int(lib().fb2_moe_ep_workspace_bytes(self.gate_up._h, self.down._h, self.max_batch, self.top_k, self.world))
+        self.workspace = self.torch.empty(n, dtype=self.torch.uint8, device=f"cuda:{self.gate_up.device}")
+        self.native = True
+        return self
+
     __call__ = forward
+

@@ -317,6 +317,23 @@ FB2_API int fb2_all_to_all_f16(fb2_comm_t *comm, fb2_stream_t stream, const fb2_
                                const size_t *send_offsets, const size_t *send_counts,
                                fb2_half *recv, const size_t *recv_offsets,
                                const size_t *recv_counts);
+/* Expert-parallel MoE FFN (the reference has no EP -- is_ep is hard-wired false,
+ * backend/cuda/quant.rs:1179 -- so parity is defined against fb2_moe_ffn_forward on one GPU).
+ * `gate_up` / `down` hold THIS rank's experts [rank*E/R, (rank+1)*E/R); x [batch_local, hidden] and
+ * router_logits [batch_local, E] are this rank's tokens (every rank passes the same batch_local).
+ * One launch routes the tokens and plans the dispatch, one scatters the rows into a fixed-capacity
+ * send buffer [R][batch_local*top_k]; one grouped all-to-all carries rows + expert ids to the expert
+ * owners; the owners run the two grouped GEMMs over the received rows; one all-to-all returns the
+ * outputs; the token owner combines.  No host sync, fixed message sizes: graph-capturable.
+ * Needs batch_local * top_k <= 1024 and E <= 256. */
+FB2_API size_t fb2_moe_ep_workspace_bytes(const fb2_stack_t *gate_up, const fb2_stack_t *down,
+                                          size_t max_batch_local, size_t top_k, int world_size);
+FB2_API int fb2_moe_ep_ffn_forward(const fb2_stack_t *gate_up, const fb2_stack_t *down,
+                                   fb2_comm_t *comm, fb2_stream_t stream, const fb2_half *x,
+                                   const fb2_half *router_logits, fb2_half *out,
+                                   size_t batch_local, size_t top_k, int norm_topk_prob,
+                                   void *workspace, size_t workspace_bytes);
+
 /* Collective over all ranks (synchronises `stream`): allocates this rank's receive buffer for
  * one-shot all-reduces of up to `max_elems` halves and maps every peer's buffer (CUDA IPC).
  * Afterwards fb2_gptq_linear_forward_allreduce pushes the GEMM's output tiles to the peers from its

@@ -127,6 +127,15 @@ def main():
     y_ep_c = ep_c.forward(torch.from_numpy(xs[sl].astype(np.float16)).to(dev), torch.from_numpy(lg[sl].astype(np.float16)).to(dev))
     torch.cuda.synchronize()
     assert torch.equal(y_ep_c, y_ep), "EP through fb2_all_to_all_f16 != EP through torch.distributed"
+    # the same layer inside the library: fb2_moe_ep_ffn_forward (route+plan, scatter, grouped all-to-all,
+    # align, two grouped GEMMs, all-to-all, combine)
+    ep_n = par.ExpertParallelFfn(mk(gus[rank * e_loc:(rank + 1) * e_loc], H, 2 * I), mk(dns[rank * e_loc:(rank + 1) * e_loc], I, H),
+                                 K, True, B // world, E, rank, world, comm=comm).enable_native()
+    y_ep_n = ep_n.forward(torch.from_numpy(xs[sl].astype(np.float16)).to(dev), torch.from_numpy(lg[sl].astype(np.float16)).to(dev))
+    torch.cuda.synchronize()
+    dn_ = (y_ep_n.float() - y_ref[sl].float()).abs().max().item() / max(y_ref.float().abs().max().item(), 1e-6)
+    assert dn_ < 2e-3, f"fb2_moe_ep_ffn_forward vs single-GPU rel {dn_}"
+    assert torch.equal(y_ep_n, y_ep), "fb2_moe_ep_ffn_forward != the torch-level EP path"
     # ---------------- fused all-reduce: GEMM epilogue pushes its tiles to the peers (NVLink, IPC-mapped
     # buffers), one reduce kernel completes the sum.  Must match the NCCL path (same fp16 partials; the
     # sum is taken in fp32 in rank order) and be bit-identical under CUDA-graph replay.
