@@ -362,7 +362,7 @@ def run_gpu(args):
     if not args.quick and not args.no_tp_prefill:
         del lins
         torch.cuda.empty_cache()
-        tp_prefill = run_tp_prefill(args, fb2, par, rank, world, local, pk)
+        tp_prefill = run_tp_prefill(args, fb2, par, rank, world, local, pk, comm)
 
     # ---------------------------------------------------------------------- MoE series
     moe = None
@@ -414,7 +414,7 @@ def run_gpu(args):
         os._exit(0)
 
 
-def run_tp_prefill(args, fb2, par, rank, world, local, pk):
+def run_tp_prefill(args, fb2, par, rank, world, local, pk, comm=None):
     """Gemma3-27B GPTQ-Int4 dense linears, prefill M tokens, tensor parallel over `world` GPUs:
     qkv (column) -> o (row + all-reduce) -> gate_up (column) -> GELU-tanh*up (local) -> down (row +
     all-reduce).  Act-order on every layer; row-parallel shards are cut in g_idx-sorted order."""
@@ -444,10 +444,10 @@ def run_tp_prefill(args, fb2, par, rank, world, local, pk):
         for m in mods:
             m["qkv_proj"].forward(x, qkv, M)
             attn.copy_(qkv[:, : Q // world])                   # stand-in for attention: the local q heads
-            m["o_proj"].forward(attn, h1, M)                   # + all-reduce
+            m["o_proj"].forward(attn, h1, M, comm)             # + all-reduce
             m["gate_up_proj"].forward(h1, gu, M)
             fb2.moe.fused_gelu_tanh_mul_split(gu, act, M, I // world)
-            m["down_proj"].forward(act, h2, M)                 # + all-reduce
+            m["down_proj"].forward(act, h2, M, comm)           # + all-reduce
     g = capture(fn)
     t = time_graph(g, 3, 2, world) / 3                         # ms per pass over `layers` layers
     flops = 2.0 * M * sum(k * n for (_, k, n) in GEMMA3["linears"]) * layers
@@ -455,7 +455,8 @@ def run_tp_prefill(args, fb2, par, rank, world, local, pk):
     del g
     return {"M": M, "layers": layers, "tflops_total": round(tf, 1), "tflops_per_gpu": round(tf / world, 1),
             "frac_tensor_per_gpu": round(tf / world / pk["tflops_sustained"], 4), "ms_per_layer": round(t / layers, 3),
-            "parallelism": f"tp{world}", "all_reduce": "nccl (torch.distributed), fp16 [M, hidden], 2 per layer"}
+            "parallelism": f"tp{world}",
+            "all_reduce": "fb2_gptq_linear_forward_allreduce (ncclAllReduce through the library communicator), fp16 [M, hidden], 2 per layer"}
 
 
 def run_moe(args, fb2, par, rank, world, local, pk, comm=None):

@@ -550,9 +550,10 @@ int fb2_gptq_linear_forward_allreduce(const fb2_linear_t *lin, fb2_comm_t *comm,
     }
     if (rc != FB2_ERR_UNSUPPORTED) return rc;
   }
+  const size_t n_out = fb2_gptq_linear_out_features(lin);
   int rc = fb2_gptq_linear_forward(lin, stream, x, y, m);
   if (rc) return rc;
-  return fb2_all_reduce_f16(comm, stream, y, m * fb2_gptq_linear_out_features(lin));
+  return fb2_all_reduce_f16(comm, stream, y, m * n_out);
 }
 
 }  // extern "C"

@@ -278,6 +278,10 @@ class TensorParallelLinear:
         self.linear = GptqLinear.from_raw(qw, sc, qz, gi, bias, bits, group, kl, nl, device=device)
 
     def forward(self, x, out=None, m=None, comm=None):
+        if self.row_parallel and self.world > 1 and comm is not None and out is not None:
+            # library path (fb2_gptq_linear_forward_allreduce): fused push all-reduce for decode-sized
+            # outputs, GEMM + ncclAllReduce through the library communicator otherwise
+            return comm.forward_allreduce(self.linear, x, out, m if m is not None else x.shape[0])
         y = self.linear.forward(x, out, m)
         if self.row_parallel and self.world > 1:
             all_reduce_(y, comm)

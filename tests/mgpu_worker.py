@@ -180,6 +180,18 @@ def main():
     t_nccl = timed(lambda: t_dn.forward(act_loc, y_p, m))
     if rank == 0:
         print(f"row-parallel down_proj K={inter}/{world} N={hidden} M={m}: fused push all-reduce {t_fused:.1f} us, GEMM + NCCL all-reduce {t_nccl:.1f} us")
+    # prefill-sized rows through the same entry point (NCCL all-reduce; the fused push is for <= 64 rows)
+    mb = 1100
+    act_big = torch.from_numpy(oracle.f16_round(oracle.lcg_f32_array(31, mb * inter, -1.0, 1.0)).reshape(mb, inter).astype(np.float16)).to(dev)
+    y_big_full = l_dn.forward(act_big)
+    act_big_loc = act_big[:, torch.from_numpy(cols.astype(np.int64)).to(dev)].contiguous()
+    y_big = torch.empty((mb, hidden), dtype=torch.float16, device=dev)
+    fb2.pregrow_scratch(local, mb)
+    ffi.check(ffi.lib().fb2_gptq_linear_forward_allreduce(h, comm._h, torch.cuda.current_stream().cuda_stream,
+                                                           act_big_loc.data_ptr(), y_big.data_ptr(), mb))
+    torch.cuda.synchronize()
+    relb = (y_big.float() - y_big_full.float()).abs().max().item() / y_big_full.float().abs().max().item()
+    assert relb < 2e-3, f"prefill-sized forward_allreduce vs single-GPU rel {relb}"
     ffi.lib().fb2_gptq_linear_destroy(h)
     comm.close()
     dist.barrier()
