@@ -201,3 +201,22 @@ def test_graph_capture_and_replay(fb2, oracle, cuda):
         g.replay()
     cuda.cuda.synchronize()
     assert cuda.equal(y, eager)      # deterministic split-K: bit-identical replays
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_batch_pageable_and_pinned(fb2, oracle, cuda, pinned):
+    """fb2_gptq_linear_forward_host_batch: 40 linears (three chunks of the H2D / GEMM / D2H pipeline,
+    the last one partial) from pageable host buffers (staged) and from page-locked ones (direct DMA);
+    both must equal the device-buffer forward bit for bit."""
+    torch = cuda
+    k, n, m = 512, 256, 5
+    syn, gi = _make(oracle, k, n, 128, 0x51, "rand")
+    lin = fb2.GptqLinear.from_raw(syn.qweight, syn.scales, syn.qzeros, gi, None, 4, 128, k, n)
+    lins = [lin] * 40
+    mk = (lambda a: torch.from_numpy(a).pin_memory().numpy()) if pinned else (lambda a: a)
+    xs = [mk(oracle.f16_round(oracle.lcg_f32_array(100 + i, m * k, -1.0, 1.0)).reshape(m, k).astype(np.float16)) for i in range(40)]
+    outs = [mk(np.zeros((m, n), dtype=np.float16)) for _ in range(40)]
+    fb2.forward_host_batch(lins, xs, m, outs)
+    for i in (0, 15, 16, 39):
+        ref = lin.forward(torch.from_numpy(np.ascontiguousarray(xs[i])).cuda()).cpu().numpy()
+        assert np.array_equal(outs[i].view(np.uint16), ref.view(np.uint16)), i
