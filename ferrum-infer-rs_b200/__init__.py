@@ -15,3 +15,4 @@ from .gptq import (QuantConfig, GptqLinear, StackedExpertLinear, GptqExpertStack
 from . import moe  # noqa: F401
 
 __version__ = "0.1.0"
+from .checkpoint import NativeSafetensorsLoader  # noqa: F401,E402

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("FB2_LIB") or os.path.join(_HERE, "libfb2_w4a16.so")
 
 FB2_OK = 0
 ERR_NAMES = {-1: "FB2_ERR_SHAPE", -2: "FB2_ERR_UNSUPPORTED", -3: "FB2_ERR_CUDA",
-             -4: "FB2_ERR_NCCL", -5: "FB2_ERR_ARG", -6: "FB2_ERR_MODEL"}
+             -4: "FB2_ERR_NCCL", -5: "FB2_ERR_ARG", -6: "FB2_ERR_MODEL", -7: "FB2_ERR_IO"}
 
 
 class Fb2Error(RuntimeError):
@@ -26,6 +26,16 @@ class Fb2Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
         self.code = code
+
+
+class QuantConfigC(C.Structure):
+    _fields_ = [("present", C.c_int), ("method", C.c_int), ("bits", C.c_uint32), ("group_size", C.c_size_t),
+                ("desc_act", C.c_int), ("sym", C.c_int)]
+
+
+class GptqInfoC(C.Structure):
+    _fields_ = [("k", C.c_size_t), ("n", C.c_size_t), ("has_g_idx", C.c_int), ("has_bias", C.c_int),
+                ("desc_act", C.c_int), ("n_parts", C.c_int), ("part_n", C.c_size_t * 4)]
 
 
 class Dispatch(C.Structure):
@@ -94,6 +104,24 @@ SIGNATURES = {
     "fb2_comm_enable_p2p": (_i32, [_vp, _vp, _sz]),
     "fb2_moe_ep_workspace_bytes": (_sz, [_vp, _vp, _sz, _sz, _i32]),
     "fb2_moe_ep_ffn_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _i32, _vp, _sz]),
+    "fb2_ckpt_open": (_i32, [C.c_char_p, C.POINTER(_vp)]),
+    "fb2_ckpt_close": (None, [_vp]),
+    "fb2_ckpt_quant_config": (_i32, [_vp, C.POINTER(QuantConfigC)]),
+    "fb2_ckpt_num_tensors": (_sz, [_vp]),
+    "fb2_ckpt_tensor_name": (C.c_char_p, [_vp, _sz]),
+    "fb2_ckpt_has_tensor": (_i32, [_vp, C.c_char_p]),
+    "fb2_ckpt_tensor_info": (_i32, [_vp, C.c_char_p, C.POINTER(_i32), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
+    "fb2_ckpt_read_f32": (_i32, [_vp, C.c_char_p, _vp, _sz]),
+    "fb2_ckpt_read_i32": (_i32, [_vp, C.c_char_p, _vp, _sz]),
+    "fb2_ckpt_gptq_info": (_i32, [_vp, C.c_char_p, C.POINTER(GptqInfoC)]),
+    "fb2_ckpt_read_gptq": (_i32, [_vp, C.c_char_p, _vp, _vp, _vp, _vp, _vp]),
+    "fb2_ckpt_load_gptq_linear": (_i32, [_vp, C.c_char_p, _i32, C.POINTER(_vp)]),
+    "fb2_ckpt_load_gptq_linear_sharded": (_i32, [_vp, C.c_char_p, _i32, _i32, _i32, _i32, _vp, C.POINTER(_vp)]),
+    "fb2_ckpt_stacked_gptq_info": (_i32, [_vp, C.c_char_p, _vp, _sz, _sz, C.POINTER(_sz), C.POINTER(_sz),
+                                          C.POINTER(_i32)]),
+    "fb2_ckpt_read_stacked_gptq_expert": (_i32, [_vp, C.c_char_p, _vp, _sz, _sz, _vp, _vp, _vp, _vp]),
+    "fb2_ckpt_load_stacked_gptq_experts": (_i32, [_vp, C.c_char_p, _sz, _sz, _vp, _sz, _i32, C.POINTER(_vp),
+                                                  C.POINTER(_sz), C.POINTER(_sz)]),
 }
 
 _lib = None

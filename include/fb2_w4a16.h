@@ -344,6 +344,88 @@ FB2_API int fb2_gptq_linear_forward_allreduce(const fb2_linear_t *lin, fb2_comm_
                                               fb2_stream_t stream, const fb2_half *x,
                                               fb2_half *y, size_t m);
 
+/* ------------------------------------------------------------------------------------
+ * Safetensors GPTQ checkpoint ingest (host C++).  Replaces NativeSafetensorsLoader
+ * (crates/ferrum-quantization/src/native_safetensors.rs): open + shard index :142-194, typed
+ * reads :197-329, read_gptq_raw :342-365, load_stacked_gptq_experts :388-585, the GPTQ branch
+ * of load_linear with its fusion shims :597-634, load_gptq_linear :763-880,
+ * load_gptq_linear_fused :887-1102, quantize_config.json / config.json :1475-1530.
+ * Semantics kept: `model.safetensors` wins over `model.safetensors.index.json`; shard files
+ * are the sorted distinct values of weight_map; sym=true 4-bit checkpoints get
+ * qzeros = 0x77777777 (:1242-1246); g_idx is validated as validate_gptq_g_idx does
+ * (:1288-1325); `<prefix>qkv_proj` / `gate_up_proj` / `in_proj_qkvz` / `in_proj_ba` are
+ * synthesised from their parts by concatenation along N when the fused tensor is absent;
+ * biases are all-or-none across fused parts.  Errors: missing files / read failures ->
+ * FB2_ERR_IO (FerrumError::io); everything malformed -> FB2_ERR_MODEL.
+ * The fb2_ckpt_read_* / *_info calls are pure host code (no GPU needed).
+ * ---------------------------------------------------------------------------------- */
+typedef struct fb2_ckpt fb2_ckpt_t;
+enum { FB2_ERR_IO = -7 };
+enum { FB2_QUANT_NONE = 0, FB2_QUANT_GPTQ = 1, FB2_QUANT_AWQ = 2, FB2_QUANT_GGUF = 3 };
+enum { FB2_DTYPE_OTHER = -1, FB2_DTYPE_F32 = 0, FB2_DTYPE_F16 = 1, FB2_DTYPE_BF16 = 2, FB2_DTYPE_I32 = 3 };
+#define FB2_MAX_RANK 8
+/* QuantConfig (crates/ferrum-quantization/src/config.rs:26-45); present = 0 when the
+ * directory carries no quantisation metadata. */
+typedef struct {
+  int present;
+  int method;
+  uint32_t bits;
+  size_t group_size;
+  int desc_act;
+  int sym;
+} fb2_quant_config_t;
+/* One GPTQ linear as load_gptq will receive it (after fusion): part_n = widths of the fused
+ * parts along N (n_parts = 1 for a stored tensor); desc_act = g_idx is a non-trivial order. */
+typedef struct {
+  size_t k, n;
+  int has_g_idx, has_bias, desc_act, n_parts;
+  size_t part_n[4];
+} fb2_gptq_info_t;
+
+FB2_API int fb2_ckpt_open(const char *model_dir, fb2_ckpt_t **out);
+FB2_API void fb2_ckpt_close(fb2_ckpt_t *ckpt);
+FB2_API int fb2_ckpt_quant_config(const fb2_ckpt_t *ckpt, fb2_quant_config_t *out);
+FB2_API size_t fb2_ckpt_num_tensors(const fb2_ckpt_t *ckpt);
+FB2_API const char *fb2_ckpt_tensor_name(const fb2_ckpt_t *ckpt, size_t i);
+FB2_API int fb2_ckpt_has_tensor(const fb2_ckpt_t *ckpt, const char *name);
+/* shape must have room for FB2_MAX_RANK entries; any out pointer may be NULL. */
+FB2_API int fb2_ckpt_tensor_info(const fb2_ckpt_t *ckpt, const char *name, int *dtype, size_t *rank,
+                                 size_t *shape, size_t *nbytes);
+/* F32 / F16 / BF16 -> f32 (read_f32, :197); I32 only (read_i32, :305).  capacity in elements. */
+FB2_API int fb2_ckpt_read_f32(const fb2_ckpt_t *ckpt, const char *name, float *out, size_t capacity);
+FB2_API int fb2_ckpt_read_i32(const fb2_ckpt_t *ckpt, const char *name, int32_t *out, size_t capacity);
+/* Resolve `name` (stored or fused) and report / copy out the host tensors exactly as they are
+ * handed to load_gptq: qweight [k/8, n], scales [k/g, n] f32, qzeros [k/g, n/8], g_idx [k]
+ * (when has_g_idx), bias [n] (when has_bias).  Output pointers may be NULL to skip a tensor. */
+FB2_API int fb2_ckpt_gptq_info(const fb2_ckpt_t *ckpt, const char *name, fb2_gptq_info_t *info);
+FB2_API int fb2_ckpt_read_gptq(const fb2_ckpt_t *ckpt, const char *name, int32_t *qweight, float *scales,
+                               int32_t *qzeros, int32_t *g_idx, float *bias);
+/* WeightLoader::load_linear for a GPTQ layer: read + fb2_gptq_linear_create. */
+FB2_API int fb2_ckpt_load_gptq_linear(const fb2_ckpt_t *ckpt, const char *name, int device,
+                                      fb2_linear_t **out);
+/* The same for this rank's tensor-parallel shard; for a column split the fused parts are the
+ * segments (q|k|v and gate|up are split separately, tp_sharding_test.rs:7-52,114-134). */
+FB2_API int fb2_ckpt_load_gptq_linear_sharded(const fb2_ckpt_t *ckpt, const char *name, int device,
+                                              int tp_rank, int tp_size, int split,
+                                              int32_t *x_cols_out, fb2_linear_t **out);
+/* load_stacked_gptq_experts (:388): expert e's tensors are `<fmt with {e} replaced><proj>` for
+ * each proj in order, concatenated along N (Qwen3-MoE: fmt "model.layers.L.mlp.experts.{e}.",
+ * projs {"gate_proj","up_proj"} and {"down_proj"}, qwen3_moe/load.rs:237-256).  Experts
+ * [expert_begin, expert_begin + num_experts) are loaded (an expert-parallel rank passes its
+ * own range).  The *_info / read_* forms are host-only views of one expert. */
+FB2_API int fb2_ckpt_stacked_gptq_info(const fb2_ckpt_t *ckpt, const char *expert_prefix_fmt,
+                                       const char *const *proj_names, size_t n_proj, size_t expert,
+                                       size_t *k, size_t *n_per_expert, int *has_g_idx);
+FB2_API int fb2_ckpt_read_stacked_gptq_expert(const fb2_ckpt_t *ckpt, const char *expert_prefix_fmt,
+                                              const char *const *proj_names, size_t n_proj,
+                                              size_t expert, int32_t *qweight, float *scales,
+                                              int32_t *qzeros, int32_t *g_idx);
+FB2_API int fb2_ckpt_load_stacked_gptq_experts(const fb2_ckpt_t *ckpt, const char *expert_prefix_fmt,
+                                               size_t expert_begin, size_t num_experts,
+                                               const char *const *proj_names, size_t n_proj,
+                                               int device, fb2_stack_t **out, size_t *n_per_expert,
+                                               size_t *k);
+
 #ifdef __cplusplus
 }
 #endif

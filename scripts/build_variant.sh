@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../ferrum-infer-rs_b200/csrc"
 name=$1; flags=$2
 out=build/variants/$name; mkdir -p $out
-for f in api generic_kernels moe_kernels tc_gemm parallel; do
+for f in api generic_kernels moe_kernels tc_gemm parallel checkpoint; do
   /usr/local/cuda/bin/nvcc $flags -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo \
     -Xcompiler -fPIC,-fvisibility=hidden -c $f.cu -o $out/$f.o &
 done
