@@ -57,6 +57,7 @@ struct DeviceScratch {
   size_t want_counters = 0;
   __half *xperm = nullptr;         // act-order: activations with columns gathered into sorted-k order
   size_t xperm_bytes = 0;
+  uint32_t *ll = nullptr;          // flag-in-value partial slots (fixed size, all-ones = empty)
 };
 static DeviceScratch g_scratch[kMaxDevices];
 
@@ -87,6 +88,14 @@ static int probe_device(int device) {
       return FB2_ERR_CUDA;
     }
     s.sm_count = prop.multiProcessorCount;
+    // FB2_DEBUG_NO_LL=1 keeps every split tile on the counter exchange (a measurement aid)
+    const char *no_ll = getenv("FB2_DEBUG_NO_LL");
+    if (!(no_ll && no_ll[0] == '1')) {
+      FB2_CUDA_TRY(cudaSetDevice(device));
+      FB2_CUDA_TRY(cudaMalloc((void **)&s.ll, kLlBytes));
+      FB2_CUDA_TRY(cudaMemset(s.ll, 0xff, kLlBytes));
+      FB2_CUDA_TRY(cudaDeviceSynchronize());
+    }
     s.probed = true;
   }
   FB2_CUDA_TRY(cudaSetDevice(device));
@@ -133,7 +142,7 @@ static TcScratch current_scratch(int device, int *sm_count) {
   DeviceScratch &s = g_scratch[device];
   std::lock_guard<std::mutex> lock(s.mu);
   if (sm_count) *sm_count = s.sm_count;
-  return TcScratch{s.partials, s.partial_bytes, s.counters, s.num_counters};
+  return TcScratch{s.partials, s.partial_bytes, s.counters, s.num_counters, s.ll, s.ll ? kLlMaxCtas : 0};
 }
 
 // -------------------------------------------------------------------- repack kernels

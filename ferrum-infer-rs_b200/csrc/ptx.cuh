@@ -189,6 +189,12 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -258,6 +264,15 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
 // barrier, the CTA's) earlier global writes before the counter update; no round trip
 __device__ __forceinline__ void red_release_add(int *addr, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+// relaxed gpu-scope accesses (L2, never L1): the flag-in-value split-tile exchange polls with these
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const void *addr) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(void *addr, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *addr) {
   uint32_t v;

@@ -104,6 +104,8 @@ struct TcParams {
   __half *y;
   float *partials;        // [grid][NACC * NB * 128]: a CTA publishes at most one partial tile
   int32_t *counters;      // [row blocks * n_tiles], zero between launches
+  uint32_t *ll;           // [ll_ctas][2 acc][kLlRows][128] flag-in-value partial slots (all kLlEmpty between launches)
+  int ll_ctas;            // CTAs the ll area serves (0: exchange disabled)
   int n_tiles;            // output tiles per row block (N/128, or I/128 with the SiLU epilogue)
   int groups;             // K / 128
   int tiles_per_expert;   // ld / 128
@@ -121,6 +123,19 @@ enum { BAR_FULL_W = 0, BAR_EMPTY_W = kMaxWStages, BAR_FULL_X = 2 * kMaxWStages,
 static_assert(BAR_COUNT * 8 <= 512, "barrier area too small");
 
 __device__ __forceinline__ float silu_mul(float g, float u) { return (g / (1.0f + expf(-g))) * u; }
+
+// Split tiles of blocks with at most kLlRows real rows (decode batches of 1-4, MoE blocks with a few
+// pairs) exchange their partial sums through FLAG-IN-VALUE slots: a slot holds kLlEmpty until the
+// contributor's plain 4-byte store lands, the tile owner polls the slots of all contributors at once,
+// sums them in contributor order and writes kLlEmpty back.  No counter, no release fence, no CTA
+// barrier on either side, and only the real rows travel.  kLlEmpty is a NaN bit pattern arithmetic
+// never produces (hardware NaNs are 0x7fffffff); a contributor maps it to that canonical NaN anyway.
+constexpr int kLlRows = 4;             // blocks with at most this many real rows use the exchange (two
+                                       // polling rounds -- 8, 16 rows -- measured slower than the counter exchange)
+constexpr int kLlGroup = 4;            // rows exchanged per polling round
+constexpr uint32_t kLlEmpty = 0xffffffffu;
+constexpr int kLlFloatsPerCta = 2 * kLlRows * kTileN;
+static_assert((size_t)kLlMaxCtas * kLlFloatsPerCta * sizeof(uint32_t) == kLlBytes, "ll area size");
 
 // Dequantise one packed word (nibble p holds k offset {0,2,4,6,1,3,5,7}[p]) into 4 half2
 // registers (k0,k1) (k2,k3) (k4,k5) (k6,k7).
@@ -604,14 +619,20 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       const int r_begin = sg.r0, r_end = sg.r1;                  // [r_begin, r_end) of [0, upt)
       const int blk = sg.blk, tile = sg.tile, tau = sg.blk * n_tiles + sg.tile;
       FB2_TL(4);
-
-      ptx::mbar_wait(bar(BAR_ACC), seg & 1);
-
-      FB2_TL(5);
-      seg++;
-      ptx::tc_fence_after();
-      // The accumulator is read in chunks of CH columns (activation rows) so that the same code
-      // serves NB = 16 ... 256 without holding NB/2 floats per thread.
+      // Everything that does not need the accumulator is resolved while the last MMAs drain.
+      // Real rows of this block: they form a prefix (dense: m; dispatch: entry.m; routed:
+      // moe_align_block_size puts real ids first), so one count describes every thread's rows.
+      int nv;
+      if (p.rm.mode == ROWS_DENSE) {
+        nv = min(NB, p.rm.m - blk * NB);
+      } else if (p.rm.mode == ROWS_DISPATCH) {
+        nv = min(NB, tbl->e[blk].m);
+      } else {
+        int c = 0;
+        for (int i = lane; i < p.rm.block; i += 32)
+          c += __ldcg(p.rm.sorted_ids + (size_t)blk * p.rm.block + i) < p.rm.num_valid ? 1 : 0;
+        nv = min(NB, __reduce_add_sync(0xffffffffu, c));
+      }
       constexpr int CH = HALF < 16 ? HALF : 16;
       constexpr int NCH = HALF / CH;
       constexpr int kPart = NACC * NB * kTileN;
@@ -627,8 +648,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       // c_first -- whose piece of the tile is the LAST segment of its range -- owns the tile: it
       // keeps its own accumulator in registers, waits until the others have published their fp32
       // partials and sums them in contributor order (deterministic).  The others (for them the
-      // tile is the FIRST segment of their range) store a partial and bump the tile counter with a
-      // fire-and-forget release increment, so they never stall in mid-stream.
+      // tile is the FIRST segment of their range) publish a partial and never stall in mid-stream.
       int c_first = cta, c_last = cta;
       if (!whole) {
         const long long tile_u0 = (long long)tau * upt;
@@ -636,87 +656,190 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         c_last = cta_of_unit(tile_u0 + upt - 1, T, G);
       }
       const bool owner = !whole && cta == c_first;
-      if (owner) {
-
-        if (threadIdx.x == 0) {
-          const int need = c_last - c_first;
-#ifdef FB2_WAIT_TIMEOUT
-          const long long t0 = clock64();
-#endif
-          while (ptx::ld_acquire(p.counters + tau) < need) {
-#ifdef FB2_WAIT_TIMEOUT
-            if (clock64() - t0 > 4000000000LL) { printf("fb2: tile counter wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
-#endif
-          }
-          p.counters[tau] = 0;                                   // self-reset for the next launch
+      // exchange protocol of this tile (identical in all of its contributors: nv depends on the block only)
+      const bool ll = !whole && NB <= 64 && nv <= kLlRows && G <= p.ll_ctas;
+      auto store_out = [&](int row_in_block, float v0, float v1) {
+        int ar, cr;
+        if (!rowmap_resolve(p.rm, tbl, NB, blk, row_in_block, ar, cr)) return;
+        const float o = kSilu ? silu_mul(v0, v1) : v0 + bias;
+        if (push_world(p) == 0) {
+          p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
+        } else {
+          const __half hv = __float2half_rn(o);
+          for (int r = 0; r < push_world(p); r++) p.push.data[r][push_off + (size_t)cr * p.ld_out + col] = hv;
         }
-        __syncwarp();                                            // reconverge before .sync.aligned tcgen05.ld
-        ptx::named_bar_sync(1, kDequantWarps * 32);
-      }
-      float *part = p.partials + (size_t)cta * kPart;
+      };
+
+      ptx::mbar_wait(bar(BAR_ACC), seg & 1);
+
+      FB2_TL(5);
+      seg++;
+      ptx::tc_fence_after();
+      if (ll) {
+        // ---- flag-in-value exchange, four rows at a time (this thread's rows: its half of the block)
+        const int row_end = min(nv, (h + 1) * HALF);             // warp-uniform loop bounds
 #pragma unroll 1
-      for (int ch = 0; ch < NCH; ch++) {
-        float v[NACC][CH];
+        for (int jr = h * HALF; jr < row_end; jr += kLlGroup) {
+          const int nr = row_end - jr;                           // rows of this group: j < nr
+          float v[NACC][kLlGroup];
 #pragma unroll
-        for (int a = 0; a < NACC; a++) {
-          const bool touched = r_begin < (a + 1) * groups && r_end > a * groups;   // CTA-uniform
-          if (touched) {
-            load_acc_chunk<CH>(lane_base + a * NB + h * HALF + ch * CH, v[a]);
+          for (int a = 0; a < NACC; a++) {
+            const bool touched = r_begin < (a + 1) * groups && r_end > a * groups;   // CTA-uniform
+            if (touched) {
+              uint32_t r[kLlGroup];
+              ptx::tmem_ld_x4(lane_base + a * NB + jr, r);
+              ptx::tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < kLlGroup; j++) v[a][j] = __uint_as_float(r[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < kLlGroup; j++) v[a][j] = 0.0f;
+            }
+          }
+          auto slot_of = [&](int c, int a, int j) {
+            return p.ll + (size_t)c * kLlFloatsPerCta + (size_t)((a * kLlRows + jr + j) * kTileN + nl);
+          };
+          if (!owner) {
+#pragma unroll
+            for (int a = 0; a < NACC; a++)
+#pragma unroll
+              for (int j = 0; j < kLlGroup; j++)
+                if (j < nr) {
+                  const uint32_t u = __float_as_uint(v[a][j]);
+                  ptx::st_relaxed_u32(slot_of(cta, a, j), u == kLlEmpty ? 0x7fffffffu : u);
+                }
+          } else {
+            constexpr int UB = 8 / NACC;                         // contributors polled together
+#pragma unroll 1
+            for (int c0 = c_first + 1; c0 <= c_last; c0 += UB) {
+              uint32_t t[UB][NACC][kLlGroup];
+#pragma unroll
+              for (int i = 0; i < UB; i++)
+#pragma unroll
+                for (int a = 0; a < NACC; a++)
+#pragma unroll
+                  for (int j = 0; j < kLlGroup; j++)
+                    t[i][a][j] = (j < nr && c0 + i <= c_last) ? ptx::ld_relaxed_u32(slot_of(c0 + i, a, j)) : 0u;
+#ifdef FB2_WAIT_TIMEOUT
+              const long long t0 = clock64();
+#endif
+              for (;;) {
+                // all slots are tested first and all missing ones re-requested together: a test
+                // between two loads would serialise the round trips
+                bool pending = false;
+#pragma unroll
+                for (int i = 0; i < UB; i++)
+#pragma unroll
+                  for (int a = 0; a < NACC; a++)
+#pragma unroll
+                    for (int j = 0; j < kLlGroup; j++) pending |= t[i][a][j] == kLlEmpty;
+                if (!pending) break;
+#pragma unroll
+                for (int i = 0; i < UB; i++)
+#pragma unroll
+                  for (int a = 0; a < NACC; a++)
+#pragma unroll
+                    for (int j = 0; j < kLlGroup; j++)
+                      if (t[i][a][j] == kLlEmpty)                // only ever true for slots that were requested
+                        t[i][a][j] = ptx::ld_relaxed_u32(slot_of(c0 + i, a, j));
+#ifdef FB2_WAIT_TIMEOUT
+                if (clock64() - t0 > 4000000000LL) { printf("fb2: ll slot wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
+#endif
+              }
+#pragma unroll
+              for (int i = 0; i < UB; i++)
+#pragma unroll
+                for (int a = 0; a < NACC; a++)
+#pragma unroll
+                  for (int j = 0; j < kLlGroup; j++)
+                    if (j < nr && c0 + i <= c_last) {
+                      v[a][j] += __uint_as_float(t[i][a][j]);
+                      ptx::st_relaxed_u32(slot_of(c0 + i, a, j), kLlEmpty);   // consumed: empty again for the next launch
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < kLlGroup; j++)
+              if (j < nr) store_out(jr + j, v[0][j], v[NACC - 1][j]);
+          }
+        }
+      } else {
+        if (owner) {
+          if (threadIdx.x == 0) {
+            const int need = c_last - c_first;
+#ifdef FB2_WAIT_TIMEOUT
+            const long long t0 = clock64();
+#endif
+            while (ptx::ld_acquire(p.counters + tau) < need) {
+#ifdef FB2_WAIT_TIMEOUT
+              if (clock64() - t0 > 4000000000LL) { printf("fb2: tile counter wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
+#endif
+            }
+            p.counters[tau] = 0;                                   // self-reset for the next launch
+          }
+          __syncwarp();                                            // reconverge before .sync.aligned tcgen05.ld
+          ptx::named_bar_sync(1, kDequantWarps * 32);
+        }
+        float *part = p.partials + (size_t)cta * kPart;
+        // The accumulator is read in chunks of CH columns (activation rows) so that the same code
+        // serves NB = 16 ... 256 without holding NB/2 floats per thread.
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ch++) {
+          const int nvc = nv - (h * HALF + ch * CH);               // real rows of this chunk (warp-uniform)
+          if (nvc <= 0) break;                                     // a prefix: later chunks are empty too
+          float v[NACC][CH];
+#pragma unroll
+          for (int a = 0; a < NACC; a++) {
+            const bool touched = r_begin < (a + 1) * groups && r_end > a * groups;   // CTA-uniform
+            if (touched) {
+              load_acc_chunk<CH>(lane_base + a * NB + h * HALF + ch * CH, v[a]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; j++) v[a][j] = 0.0f;
+            }
+          }
+          const size_t row_off = (size_t)(h * HALF + ch * CH) * kTileN + nl;
+          if (owner) {
+            // UC contributors x CH rows x NACC accumulators of independent L2 loads in flight; the sums
+            // are taken in contributor order (deterministic)
+            constexpr int UC = NACC * CH <= 8 ? 4 : (NACC * CH <= 16 ? 2 : 1);
+#pragma unroll 1
+            for (int c0 = c_first + 1; c0 <= c_last; c0 += UC) {
+              float t[UC][NACC][CH];
+#pragma unroll
+              for (int i = 0; i < UC; i++) {
+                const float *src = p.partials + (size_t)(c0 + i) * kPart + row_off;
+#pragma unroll
+                for (int a = 0; a < NACC; a++)
+#pragma unroll
+                  for (int j = 0; j < CH; j++)
+                    t[i][a][j] = (j < nvc && c0 + i <= c_last) ? __ldcg(src + (size_t)(a * NB + j) * kTileN) : 0.0f;
+              }
+#pragma unroll
+              for (int i = 0; i < UC; i++)
+#pragma unroll
+                for (int a = 0; a < NACC; a++)
+#pragma unroll
+                  for (int j = 0; j < CH; j++) v[a][j] += t[i][a][j];
+            }
+          }
+          if (whole || owner) {
+#pragma unroll
+            for (int j = 0; j < CH; j++)
+              if (j < nvc) store_out(h * HALF + ch * CH + j, v[0][j], v[NACC - 1][j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < CH; j++) v[a][j] = 0.0f;
+            for (int a = 0; a < NACC; a++)
+#pragma unroll
+              for (int j = 0; j < CH; j++)
+                if (j < nvc) part[row_off + (size_t)(a * NB + j) * kTileN] = v[a][j];
           }
-        }
-        const size_t row_off = (size_t)(h * HALF + ch * CH) * kTileN + nl;
-        if (owner) {
-          // UC contributors x CH rows x NACC accumulators of independent L2 loads in flight; the sums
-          // are taken in contributor order (deterministic)
-          constexpr int UC = NACC * CH <= 8 ? 4 : (NACC * CH <= 16 ? 2 : 1);
-#pragma unroll 1
-          for (int c0 = c_first + 1; c0 <= c_last; c0 += UC) {
-            float t[UC][NACC][CH];
-#pragma unroll
-            for (int i = 0; i < UC; i++) {
-              const float *src = p.partials + (size_t)(c0 + i) * kPart + row_off;
-#pragma unroll
-              for (int a = 0; a < NACC; a++)
-#pragma unroll
-                for (int j = 0; j < CH; j++)
-                  t[i][a][j] = c0 + i <= c_last ? __ldcg(src + (size_t)(a * NB + j) * kTileN) : 0.0f;
-            }
-#pragma unroll
-            for (int i = 0; i < UC; i++)
-#pragma unroll
-              for (int a = 0; a < NACC; a++)
-#pragma unroll
-                for (int j = 0; j < CH; j++) v[a][j] += t[i][a][j];
-          }
-        }
-        if (whole || owner) {
-#pragma unroll
-          for (int j = 0; j < CH; j++) {
-            int ar, cr;
-            if (!rowmap_resolve(p.rm, tbl, NB, blk, h * HALF + ch * CH + j, ar, cr)) continue;
-            const float o = kSilu ? silu_mul(v[0][j], v[NACC - 1][j]) : v[0][j] + bias;
-            if (push_world(p) == 0) {
-              p.y[(size_t)cr * p.ld_out + col] = __float2half_rn(o);
-            } else {
-              const __half hv = __float2half_rn(o);
-              for (int r = 0; r < push_world(p); r++) p.push.data[r][push_off + (size_t)cr * p.ld_out + col] = hv;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int a = 0; a < NACC; a++)
-#pragma unroll
-            for (int j = 0; j < CH; j++) part[row_off + (size_t)(a * NB + j) * kTileN] = v[a][j];
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar(BAR_ACC_EMPTY));      // accumulators may be overwritten
       FB2_TL(6);
-      if (!whole && !owner) {
+      if (!whole && !owner && !ll) {
         ptx::named_bar_sync(1, kDequantWarps * 32);              // every partial store of the CTA is issued
         if (threadIdx.x == 0) ptx::red_release_add(p.counters + tau, 1);
         __syncwarp();
@@ -1017,6 +1140,8 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   p.y = y;
   p.partials = scratch.partials;
   p.counters = scratch.counters;
+  p.ll = scratch.ll;
+  p.ll_ctas = scratch.ll ? scratch.ll_ctas : 0;
   p.n_tiles = pl.n_tiles;
   p.groups = w.k / kGroup;
   p.tiles_per_expert = w.ld / kTileN;

@@ -6,11 +6,13 @@ import bench
 fb2 = importlib.import_module("ferrum-infer-rs_b200")
 act = bool(int(sys.argv[1])) if len(sys.argv) > 1 else True
 Ms = [int(a) for a in sys.argv[2:]] or [1]
-layers = 16
+import math
 rng = np.random.default_rng(0)
 out = {}
 for (name, k, n) in bench.LLAMA["linears"]:
     lins = []
+    # enough distinct weights to defeat the 126 MB L2
+    layers = min(48, max(4, math.ceil(400e6 / bench.alg_bytes(k, n, 1, act))))
     for _ in range(layers):
         qw, sc, qz, gi = bench.synth_gptq(rng, k, n, act_order=act)
         lins.append(fb2.GptqLinear.from_raw(qw, sc, qz, gi, None, 4, 128, k, n))
