@@ -41,6 +41,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
@@ -203,7 +204,11 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, float *v) {
 }
 
 // ---- stream-K bookkeeping (identical in every role) -------------------------------------
-__device__ __forceinline__ long long range_start(long long c, long long T, int G) { return c * T / G; }
+// All of it is 32-bit unsigned arithmetic: the host keeps (units x CTAs) below 2^31 (launch_tc_gemm cuts
+// larger dense batches into several launches).  The emulated 64-bit divisions this replaces sat on the
+// critical path twice: before the first weight request of every CTA and in front of every fix-up.
+typedef unsigned int u32;
+__device__ __forceinline__ u32 range_start(u32 c, u32 T, u32 G) { return c * T / G; }
 // Tiles of only a few units (K <= 1024: the MoE down projection has 6) are never split: cutting one
 // costs a partial-tile fix-up (~3 us) that is longer than streaming the whole tile.  CTA c then owns
 // the whole tiles [c * NT / G, (c + 1) * NT / G) -- when that balances: at most one tile per CTA, or so
@@ -212,11 +217,9 @@ constexpr int kWholeTileMaxUnits = 8;
 __host__ __device__ __forceinline__ bool whole_tile_mode(int upt, long long n_tiles_total, int slots) {
   return upt <= kWholeTileMaxUnits && (n_tiles_total <= slots || n_tiles_total >= 4LL * slots);
 }
-__device__ __forceinline__ long long tile_range_start(long long c, long long NT, int G, int upt) {
-  return (c * NT / G) * upt;
-}
-__device__ __forceinline__ int cta_of_unit(long long u, long long T, int G) {
-  long long c = u * G / T;
+__device__ __forceinline__ u32 tile_range_start(u32 c, u32 NT, u32 G, u32 upt) { return (c * NT / G) * upt; }
+__device__ __forceinline__ int cta_of_unit(u32 u, u32 T, u32 G) {
+  u32 c = u * G / T;
   while (c + 1 < G && range_start(c + 1, T, G) <= u) c++;
   while (c > 0 && range_start(c, T, G) > u) c--;
   return (int)c;
@@ -230,11 +233,11 @@ struct Seg {
 };
 struct SegIter {
   int blk, tile, r, left, first;
-  __device__ __forceinline__ void init(long long u0, long long u1, int upt, int n_tiles) {
-    const long long tau = u0 / upt;
-    r = (int)(u0 - tau * upt);
-    blk = (int)(tau / n_tiles);
-    tile = (int)(tau - (long long)blk * n_tiles);
+  __device__ __forceinline__ void init(u32 u0, u32 u1, int upt, int n_tiles) {
+    const u32 tau = u0 / (u32)upt;
+    r = (int)(u0 - tau * (u32)upt);
+    blk = (int)(tau / (u32)n_tiles);
+    tile = (int)(tau - (u32)blk * (u32)n_tiles);
     left = (int)(u1 - u0);
     first = 1;
   }
@@ -312,9 +315,9 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   // Routed mode learns its block count from the align kernel (an earlier kernel): its unit range
   // is computed after the grid dependency, i.e. after the dependency-free part of the setup.
   const bool routed = p.rm.mode == ROWS_ROUTED;
-  long long T = 0, u0 = 0, u1 = 0;
+  u32 T = 0, u0 = 0, u1 = 0;
   if (!routed) {
-    T = (long long)rowmap_num_blocks(p.rm, NB) * n_tiles * upt;
+    T = (u32)rowmap_num_blocks(p.rm, NB) * (u32)n_tiles * (u32)upt;
     if (p.whole_tiles) {                                         // host decided (it sized the grid)
       u0 = tile_range_start(cta, T / upt, G, upt);
       u1 = tile_range_start(cta + 1, T / upt, G, upt);
@@ -372,14 +375,14 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
 
   if (routed) {
     ptx::grid_dependency_wait();
-    T = (long long)rowmap_num_blocks(p.rm, NB) * n_tiles * upt;
+    T = (u32)rowmap_num_blocks(p.rm, NB) * (u32)n_tiles * (u32)upt;
     // The grid was sized for the worst-case block count; with fewer units only the first
     // max(1, T/2) CTAs take part, so that every participating CTA owns a non-empty range and the
     // contributors of a tile are exactly the consecutive CTAs c_first .. c_last.
-    const bool whole_tiles = whole_tile_mode(upt, T / upt, G);
-    const long long cap = whole_tiles ? T / upt : T / 2;           // whole tiles | >= 2 units per CTA
-    const long long g_eff = cap > 1 ? cap : 1;
-    if (g_eff < G) G = (int)g_eff;
+    const bool whole_tiles = whole_tile_mode(upt, T / (u32)upt, G);
+    const u32 cap = whole_tiles ? T / (u32)upt : T / 2;             // whole tiles | >= 2 units per CTA
+    const u32 g_eff = cap > 1 ? cap : 1;
+    if (g_eff < (u32)G) G = (int)g_eff;
     if (cta < G) {
       if (whole_tiles) {
         u0 = tile_range_start(cta, T / upt, G, upt);
@@ -651,7 +654,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       // tile is the FIRST segment of their range) publish a partial and never stall in mid-stream.
       int c_first = cta, c_last = cta;
       if (!whole) {
-        const long long tile_u0 = (long long)tau * upt;
+        const u32 tile_u0 = (u32)tau * (u32)upt;
         c_first = cta_of_unit(tile_u0, T, G);
         c_last = cta_of_unit(tile_u0 + upt - 1, T, G);
       }
@@ -929,6 +932,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const __half *__restric
 // ------------------------------------------------------------------------ host planning
 struct TcPlan {
   int nb, row_blocks, n_tiles, nacc, grid, whole_tiles;
+  long long units;
   size_t partial_floats, counters;
   uint32_t smem;
 };
@@ -961,6 +965,7 @@ TcPlan make_plan(const WeightRef &w, const RowMap &rows, int epilogue, int sm_co
   pl.nacc = epilogue ? 2 : 1;
   pl.n_tiles = (epilogue ? w.n / 2 : w.n) / kTileN;
   const long long units = (long long)pl.row_blocks * pl.n_tiles * pl.nacc * (w.k / kGroup);
+  pl.units = units;
   static const int ctas_per_sm_dbg = [] { const char *e = getenv("FB2_DEBUG_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   const int per_sm = ctas_per_sm_dbg ? ctas_per_sm_dbg : (pl.nb >= 128 ? 1 : 2);
   const int slots = per_sm * (sm_count > 0 ? sm_count : 148);
@@ -1127,6 +1132,27 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
     return FB2_ERR_ARG;
   }
   TcPlan pl = make_plan(w, rows, epilogue, sm_count);
+  // the kernels' unit bookkeeping is 32-bit: units x CTAs stays below 2^31
+  if (pl.units * pl.grid >= (1LL << 31)) {
+    if (rows.mode != ROWS_DENSE || push) {
+      set_error("launch too large for one grid (%lld units x %d CTAs)", pl.units, pl.grid);
+      return FB2_ERR_UNSUPPORTED;
+    }
+    // dense batch: cut the rows into several launches of whole row blocks
+    const long long per_block = pl.units / pl.row_blocks;
+    long long blocks = ((1LL << 31) - 1) / ((long long)pl.grid * per_block);
+    if (blocks < 1) { set_error("weight matrix too large for one grid"); return FB2_ERR_UNSUPPORTED; }
+    const size_t chunk = (size_t)blocks * pl.nb;
+    const size_t ld_out = epilogue ? w.n / 2 : w.n;
+    for (size_t r0 = 0; r0 < (size_t)rows.m; r0 += chunk) {
+      RowMap sub = rows;
+      sub.m = (int)std::min(chunk, (size_t)rows.m - r0);
+      int rc = launch_tc_gemm(w, sub, nullptr, x + r0 * w.k, (size_t)sub.m, y + r0 * ld_out, epilogue, scratch, sm_count,
+                              stream, nullptr);
+      if (rc) return rc;
+    }
+    return FB2_OK;
+  }
   if (pl.partial_floats * 4 > scratch.partial_bytes || pl.counters > scratch.num_counters) {
     set_error("split-K scratch too small (%zu > %zu bytes, %zu > %zu counters): call "
               "fb2_pregrow_scratch outside graph capture",
