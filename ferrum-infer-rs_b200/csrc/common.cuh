@@ -169,7 +169,7 @@ struct TcScratch {
   int ll_ctas;                       // CTAs the area serves; 0 = exchange disabled
 };
 constexpr int kLlMaxCtas = 1024;                 // >= 2 CTAs per SM on any sm_100 part
-constexpr size_t kLlBytes = (size_t)kLlMaxCtas * 2 * 4 * 128 * sizeof(uint32_t);   // [ctas][2 acc][4 rows][128]
+constexpr size_t kLlBytes = (size_t)kLlMaxCtas * 2 * 8 * 128 * sizeof(uint32_t);   // [ctas][2 acc][8 rows][128]
 bool tc_supported(const WeightRef &w);
 // Split-K scratch one launch with these rows needs (0 / 0 when it does not split).
 void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count,

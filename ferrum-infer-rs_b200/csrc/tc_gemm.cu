@@ -125,14 +125,15 @@ static_assert(BAR_COUNT * 8 <= 512, "barrier area too small");
 
 __device__ __forceinline__ float silu_mul(float g, float u) { return (g / (1.0f + expf(-g))) * u; }
 
-// Split tiles of blocks with at most kLlRows real rows (decode batches of 1-4, MoE blocks with a few
+// Split tiles of blocks with at most kLlRows real rows (decode batches of 1-8, MoE blocks with a few
 // pairs) exchange their partial sums through FLAG-IN-VALUE slots: a slot holds kLlEmpty until the
 // contributor's plain 4-byte store lands, the tile owner polls the slots of all contributors at once,
 // sums them in contributor order and writes kLlEmpty back.  No counter, no release fence, no CTA
 // barrier on either side, and only the real rows travel.  kLlEmpty is a NaN bit pattern arithmetic
 // never produces (hardware NaNs are 0x7fffffff); a contributor maps it to that canonical NaN anyway.
-constexpr int kLlRows = 4;             // blocks with at most this many real rows use the exchange (two
-                                       // polling rounds -- 8, 16 rows -- measured slower than the counter exchange)
+constexpr int kLlRows = 8;             // blocks with at most this many real rows use the exchange (one polling
+                                       // round per warp set; two rounds -- 16 rows -- measured slower than the
+                                       // counter exchange)
 constexpr int kLlGroup = 4;            // rows exchanged per polling round
 constexpr uint32_t kLlEmpty = 0xffffffffu;
 constexpr int kLlFloatsPerCta = 2 * kLlRows * kTileN;
@@ -679,11 +680,12 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       seg++;
       ptx::tc_fence_after();
       if (ll) {
-        // ---- flag-in-value exchange, four rows at a time (this thread's rows: its half of the block)
-        const int row_end = min(nv, (h + 1) * HALF);             // warp-uniform loop bounds
+        // ---- flag-in-value exchange, four rows at a time.  Row groups alternate between the two warp
+        // sets (any warp may read any accumulator COLUMN of its lane quarter), so eight rows still take
+        // a single polling round.
 #pragma unroll 1
-        for (int jr = h * HALF; jr < row_end; jr += kLlGroup) {
-          const int nr = row_end - jr;                           // rows of this group: j < nr
+        for (int jr = h * kLlGroup; jr < nv; jr += 2 * kLlGroup) {   // warp-uniform loop bounds
+          const int nr = nv - jr;                                // rows of this group: j < nr
           float v[NACC][kLlGroup];
 #pragma unroll
           for (int a = 0; a < NACC; a++) {
