@@ -25,6 +25,11 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrive that the compiler must keep behind the computation of `after` (a value derived from every
+// shared-memory load of the stage being released: in-order issue then guarantees the loads have landed)
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t after) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t// %1\n\t}" ::"r"(bar), "r"(after) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");

@@ -300,8 +300,8 @@ template <int NB, bool kSilu, bool kPush = false>
 __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *tbl, const CUtensorMap *xmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SC = StageCfg<NB>;
-  constexpr int kTmemCols = SC::kTmemCols, kTmemABase = SC::kTmemABase, kASlots = SC::kASlots;
   constexpr int NACC = kSilu ? 2 : 1;
+  constexpr int kTmemCols = SC::kTmemCols, kTmemABase = SC::kTmemABase, kASlots = SC::kASlots;
   constexpr int HALF = NB / 2;
   constexpr int SW = SC::kWStages, SX = SC::kXSlots;
   static_assert(SW >= 3 && SX >= 2, "smem rings too shallow");
@@ -535,7 +535,8 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
 #pragma unroll 1
         for (int g = g0; g < g1; g++, xp.advance(SX), ap.advance(kASlots)) {
           ptx::mbar_wait(bar(BAR_FULL_X + xp.st), xp.par);        // activation slice landed
-          ptx::fence_proxy_async_smem();                          // cp.async data -> async proxy
+          // gathered rows were written through the generic proxy (cp.async); TMA boxes already are async-proxy writes
+          if (!(p.x_tma & 1)) ptx::fence_proxy_async_smem();
           const uint64_t b_desc0 = b_desc_ring + (uint64_t)((xp.st * SC::kXBytes) >> 4);
           const uint32_t acc_flag = g != g0 ? 1u : 0u;            // first unit of a phase zero-inits
 #pragma unroll
@@ -612,18 +613,17 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         dequant_word(w1.z, zlo, zhi, s2, r1 + 8);
         dequant_word(w1.w, zlo, zhi, s2, r1 + 12);
         // the packed words are in registers (consumed, not merely requested): release the weight
-        // stage to the HBM stream now -- it does not wait for the MMA
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(k_ew + wp.st * 8);
+        // stage to the HBM stream now -- it does not wait for the MMA.  The arrive is predicated (no
+        // divergence, so no reconvergence point is needed) and tied to the last dequantised words.
+        if (lane == 0) ptx::mbar_arrive_after(k_ew + wp.st * 8, r0[15] ^ r1[15]);
 
         ptx::mbar_wait(k_be + ap.st * 16, ap.par ^ 1u);
         ptx::tc_fence_after();
         const uint32_t ta = k_ta + ap.st * 64;
         ptx::tmem_st_x16(ta, r0);
         ptx::tmem_st_x16(ta + 16, r1);
-        ptx::tmem_wait_st();
+        ptx::tmem_wait_st();                                      // warp-collective: every lane's stores are done
         ptx::tc_fence_before();
-        __syncwarp();
         if (lane == 0) ptx::mbar_arrive(k_bf + ap.st * 16);
       }
 
