@@ -588,8 +588,10 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     si.init(u0, u1, upt, n_tiles);
     Seg sg;
     while (si.next(sg, upt, n_tiles)) {
-#pragma unroll 1
-      for (int n = sg.r1 - sg.r0; n > 0; n--, wp.advance(SW), ap.advance(kASlots)) {
+      // One unit: a weight stage through the dequant maths into an A slot.  S >= 0 compiles the A slot in.
+      auto unit = [&](auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;
+        const uint32_t a_slot = S < 0 ? (uint32_t)ap.st : (uint32_t)S;
         const uint32_t stage_off = wp.st * kStageBytes;
         ptx::mbar_wait(k_fw + wp.st * 8, wp.par);
         if (tl_first) { FB2_TL(3); tl_first = false; }
@@ -617,14 +619,35 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         // divergence, so no reconvergence point is needed) and tied to the last dequantised words.
         if (lane == 0) ptx::mbar_arrive_after(k_ew + wp.st * 8, r0[15] ^ r1[15]);
 
-        ptx::mbar_wait(k_be + ap.st * 16, ap.par ^ 1u);
+        ptx::mbar_wait(k_be + a_slot * 16, ap.par ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t ta = k_ta + ap.st * 64;
+        const uint32_t ta = k_ta + a_slot * 64;
         ptx::tmem_st_x16(ta, r0);
         ptx::tmem_st_x16(ta + 16, r1);
         ptx::tmem_wait_st();                                      // warp-collective: every lane's stores are done
         ptx::tc_fence_before();
-        if (lane == 0) ptx::mbar_arrive(k_bf + ap.st * 16);
+        if (lane == 0) ptx::mbar_arrive(k_bf + a_slot * 16);
+        wp.advance(SW);
+      };
+      if constexpr (kASlots == 2) {
+        // Two A slots: two copies of the body alternate, each with its slot (barrier and TMEM addresses)
+        // compiled in; the ring position costs one parity flip per pair instead of ten instructions a unit.
+        int n = sg.r1 - sg.r0;
+#pragma unroll 1
+        while (n > 0) {
+          if (ap.st == 0) {
+            unit(std::integral_constant<int, 0>{});
+            ap.st = 1;
+            if (--n == 0) break;
+          }
+          unit(std::integral_constant<int, 1>{});
+          ap.st = 0;
+          ap.par ^= 1u;
+          --n;
+        }
+      } else {
+#pragma unroll 1
+        for (int n = sg.r1 - sg.r0; n > 0; n--, ap.advance(kASlots)) unit(std::integral_constant<int, -1>{});
       }
 
       // ------------------------------------------------ epilogue of this tile segment
