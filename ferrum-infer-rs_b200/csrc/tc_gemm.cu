@@ -1166,14 +1166,20 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   }
   TcPlan pl = make_plan(w, rows, epilogue, sm_count);
   // the kernels' unit bookkeeping is 32-bit: units x CTAs stays below 2^31
-  if (pl.units * pl.grid >= (1LL << 31)) {
+  // (FB2_DEBUG_MAX_UNIT_CTAS lowers the limit so that a test can reach the chunked path with a small batch)
+  static const long long unit_cta_limit = [] {
+    const char *e = getenv("FB2_DEBUG_MAX_UNIT_CTAS");
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 && v < (1LL << 31) ? v : (1LL << 31);
+  }();
+  if (pl.units * pl.grid >= unit_cta_limit) {
     if (rows.mode != ROWS_DENSE || push) {
       set_error("launch too large for one grid (%lld units x %d CTAs)", pl.units, pl.grid);
       return FB2_ERR_UNSUPPORTED;
     }
     // dense batch: cut the rows into several launches of whole row blocks
     const long long per_block = pl.units / pl.row_blocks;
-    long long blocks = ((1LL << 31) - 1) / ((long long)pl.grid * per_block);
+    long long blocks = (unit_cta_limit - 1) / ((long long)pl.grid * per_block);
     if (blocks < 1) { set_error("weight matrix too large for one grid"); return FB2_ERR_UNSUPPORTED; }
     const size_t chunk = (size_t)blocks * pl.nb;
     const size_t ld_out = epilogue ? w.n / 2 : w.n;

@@ -339,3 +339,28 @@ def test_gpu_load_stacked_experts(fb2, oracle, cuda, tmp_path):
     # an expert-parallel rank loads its own half
     half, _, _ = ld.load_stacked_gptq_experts("L.experts.{e}.", E // 2, ("gate_proj", "up_proj"), expert_begin=2)
     np.testing.assert_array_equal(half.dequantize().cpu().numpy(), w[2:])
+
+
+def test_header_json_corner_cases(fb2, tmp_path):
+    """The container header is arbitrary JSON: escapes, unicode names, nested metadata, exponents, padding."""
+    blob = np.arange(6, dtype=np.float32).tobytes()
+    name = "ténsor \"q\"\\\n\U0001F600"
+    header = {"__metadata__": {"note": "a\tb", "nested": "{\"x\": [1, 2.5e3, -1E-2, true, false, null]}"},
+              name: {"dtype": "F32", "shape": [2, 3], "data_offsets": [0, 24]},
+              "empty": {"dtype": "F16", "shape": [0, 4], "data_offsets": [24, 24]},
+              "scalar": {"dtype": "I32", "shape": [], "data_offsets": [24, 28]}}
+    for ascii_only in (True, False):
+        hj = json.dumps(header, ensure_ascii=ascii_only).encode("utf-8")
+        hj = b"  " + hj + b" \n\t  "
+        (tmp_path / "model.safetensors").write_bytes(struct.pack("<Q", len(hj)) + hj + blob + struct.pack("<i", -7))
+        ld = fb2.NativeSafetensorsLoader.open(tmp_path)
+        assert sorted(ld.tensor_names()) == sorted([name, "empty", "scalar"])
+        np.testing.assert_array_equal(ld.read_f32(name), np.arange(6, dtype=np.float32).reshape(2, 3))
+        assert ld.tensor_info("empty") == ("F16", (0, 4), 0) and ld.read_f32("empty").shape == (0, 4)
+        assert ld.tensor_info("scalar") == ("I32", (), 4) and int(ld.read_i32("scalar")) == -7
+    for bad in (b'{"t": {"dtype": "F32", "shape": [1], "data_offsets": [0, 4]},}', b'{"t": {"dtype": "F32" "shape": [1]}}',
+                b'{"t": {"dtype": "F32", "shape": [1.5], "data_offsets": [0, 4]}}', b'{"t": "x"}', b'{"a": [' * 100):
+        (tmp_path / "model.safetensors").write_bytes(struct.pack("<Q", len(bad)) + bad + b"\0" * 8)
+        with pytest.raises(fb2.Fb2Error) as e:
+            fb2.NativeSafetensorsLoader.open(tmp_path)
+        assert e.value.code == -6
