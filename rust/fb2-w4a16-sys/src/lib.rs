@@ -279,6 +279,90 @@ pub fn moe_ep_workspace_bytes(gate_up: &ExpertStack, down: &ExpertStack, max_bat
     unsafe { ffi::fb2_moe_ep_workspace_bytes(gate_up.h, down.h, max_batch_local, top_k, world_size as c_int) }
 }
 
+// --------------------------------------------------------------------------------------- moe
+/// The routing pre/post-ops of `BackendMoeFused` (capabilities.rs:305-723).  Every function appends
+/// work to `stream` and returns; all pointers are device pointers owned by the caller.
+pub mod moe {
+    use super::{check, ffi, DevF16, DevF16Mut, Result, Stream};
+    use std::os::raw::c_int;
+
+    /// `route_topk_softmax` (capabilities.rs:321; CPU `moe/router.rs:183-257`): ids `[batch, top_k]` i32,
+    /// weights `[batch, top_k]` f32; ties go to the lower expert index.
+    ///
+    /// # Safety
+    /// device pointers of the stated shapes.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn route_topk_softmax(stream: Stream, logits: DevF16, out_ids: *mut i32, out_weights: *mut f32, batch: usize,
+                                     num_experts: usize, top_k: usize, norm_topk_prob: bool) -> Result<()> {
+        check(ffi::fb2_moe_route_topk_softmax(stream, logits, out_ids, out_weights, batch, num_experts, top_k,
+                                              norm_topk_prob as c_int))
+    }
+
+    /// `moe_build_pairs_by_token` (capabilities.rs:372): deterministic (token-ascending inside an expert).
+    ///
+    /// # Safety
+    /// device pointers: `expert_ids`, `pairs_by_token`, `packed_token_idx` hold `batch_x_topk` i32;
+    /// `expert_offsets` holds `num_experts + 1`.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn build_pairs_by_token(stream: Stream, expert_ids: *const i32, pairs_by_token: *mut i32,
+                                       packed_token_idx: *mut i32, expert_offsets: *mut i32, batch_x_topk: usize,
+                                       num_experts: usize, top_k: usize) -> Result<()> {
+        check(ffi::fb2_moe_build_pairs_by_token(stream, expert_ids, pairs_by_token, packed_token_idx, expert_offsets,
+                                                batch_x_topk, num_experts, top_k))
+    }
+
+    /// `moe_align_block_size` / `moe_align_block_size_pair_ids` (capabilities.rs:389,406): `pair_ids`
+    /// selects the second convention (sorted ids are pair indices, not token indices).
+    ///
+    /// # Safety
+    /// device pointers; `sorted_token_ids` holds `sorted_max_size` i32, `block_ids` holds
+    /// `sorted_max_size / block_size`, `total_tokens_post_pad` one i32.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn align_block_size(stream: Stream, expert_ids_per_pair: *const i32, sorted_token_ids: *mut i32,
+                                   block_ids: *mut i32, total_tokens_post_pad: *mut i32, batch_x_topk: usize,
+                                   num_experts: usize, block_size: usize, sorted_max_size: usize, pair_ids: bool)
+                                   -> Result<()> {
+        check(ffi::fb2_moe_align_block_size(stream, expert_ids_per_pair, sorted_token_ids, block_ids, total_tokens_post_pad,
+                                            batch_x_topk, num_experts, block_size, sorted_max_size, pair_ids as c_int))
+    }
+
+    /// `moe_combine` (capabilities.rs:683): `out[b] = sum_k w[b,k] * packed_down[pairs_by_token[b,k]]`, fp32 sum.
+    ///
+    /// # Safety
+    /// device pointers of the stated shapes.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn combine(stream: Stream, packed_down: DevF16, pairs_by_token: *const i32, pair_weights: *const f32,
+                          out: DevF16Mut, batch: usize, hidden: usize, top_k: usize) -> Result<()> {
+        check(ffi::fb2_moe_combine(stream, packed_down, pairs_by_token, pair_weights, out, batch, hidden, top_k))
+    }
+
+    /// `weighted_sum_batched` (capabilities.rs:571): slots `[batch, top_k, hidden]`.
+    ///
+    /// # Safety
+    /// device pointers of the stated shapes.
+    pub unsafe fn weighted_sum_batched(stream: Stream, slots: DevF16, weights: *const f32, out: DevF16Mut, batch: usize,
+                                       top_k: usize, hidden: usize) -> Result<()> {
+        check(ffi::fb2_moe_weighted_sum_batched(stream, slots, weights, out, batch, top_k, hidden))
+    }
+
+    /// `fused_silu_mul_split` (backend/cpu.rs:1666): `[tokens, 2*im]` -> `[tokens, im]`.
+    ///
+    /// # Safety
+    /// device pointers of the stated shapes.
+    pub unsafe fn fused_silu_mul_split(stream: Stream, gate_up: DevF16, out: DevF16Mut, tokens: usize, im: usize) -> Result<()> {
+        check(ffi::fb2_fused_silu_mul_split(stream, gate_up, out, tokens, im))
+    }
+
+    /// The Gemma form of the same op (`fused_gelu_tanh_mul_split`).
+    ///
+    /// # Safety
+    /// device pointers of the stated shapes.
+    pub unsafe fn fused_gelu_tanh_mul_split(stream: Stream, gate_up: DevF16, out: DevF16Mut, tokens: usize, im: usize)
+                                            -> Result<()> {
+        check(ffi::fb2_fused_gelu_tanh_mul_split(stream, gate_up, out, tokens, im))
+    }
+}
+
 // -------------------------------------------------------------------------------------- comm
 /// One NCCL communicator per process (`NcclRank`, nccl_comm.rs:12-105; `BackendCollective`, capabilities.rs:85-107).
 pub struct Comm { h: *mut ffi::Fb2Comm }

@@ -228,3 +228,163 @@ pub fn moe_ffn_forward(ctx: &mut CudaState, gate_up: &dyn MarlinExpertStack<Cuda
     }
     .map_err(|e| ferr("fb2 moe_ffn_forward", e))
 }
+
+// ---------------------------------------------------------------- BackendMoeFused entry points
+// Bodies for `impl BackendMoeFused for CudaBackend` (backend/cuda/moe.rs:145-560).  Buffer dtypes follow
+// that impl: logits / activations F16, ids and index arrays I32, routing weights F32.
+
+/// `route_topk_softmax` (capabilities.rs:321, CUDA impl moe.rs:146).
+#[allow(clippy::too_many_arguments)]
+pub fn route_topk_softmax(ctx: &mut CudaState, logits: &CudaBuf, out_ids: &mut CudaBuf, out_weights: &mut CudaBuf,
+                          batch: usize, num_experts: usize, top_k: usize, norm_topk_prob: bool) -> Result<()> {
+    let stream = ctx.stream.clone();
+    let (l, _g0) = logits.as_f16().device_ptr(&stream);
+    let (i, _g1) = out_ids.as_i32_mut().device_ptr_mut(&stream);
+    let (w, _g2) = out_weights.as_f32_mut().device_ptr_mut(&stream);
+    unsafe {
+        fb2::moe::route_topk_softmax(raw_stream(ctx), l as fb2::DevF16, i as *mut i32, w as *mut f32, batch, num_experts,
+                                     top_k, norm_topk_prob)
+    }
+    .map_err(|e| ferr("fb2 route_topk_softmax", e))
+}
+
+/// `moe_build_pairs_by_token` (capabilities.rs:372, CUDA impl moe.rs:314).
+#[allow(clippy::too_many_arguments)]
+pub fn moe_build_pairs_by_token(ctx: &mut CudaState, expert_ids: &CudaBuf, pairs_by_token: &mut CudaBuf,
+                                packed_token_idx: &mut CudaBuf, expert_offsets: &mut CudaBuf, batch_x_topk: usize,
+                                num_experts: usize, top_k: usize) -> Result<()> {
+    let stream = ctx.stream.clone();
+    let (e, _g0) = expert_ids.as_i32().device_ptr(&stream);
+    let (p, _g1) = pairs_by_token.as_i32_mut().device_ptr_mut(&stream);
+    let (t, _g2) = packed_token_idx.as_i32_mut().device_ptr_mut(&stream);
+    let (o, _g3) = expert_offsets.as_i32_mut().device_ptr_mut(&stream);
+    unsafe {
+        fb2::moe::build_pairs_by_token(raw_stream(ctx), e as *const i32, p as *mut i32, t as *mut i32, o as *mut i32,
+                                       batch_x_topk, num_experts, top_k)
+    }
+    .map_err(|e| ferr("fb2 moe_build_pairs_by_token", e))
+}
+
+#[allow(clippy::too_many_arguments)]
+fn align_impl(ctx: &mut CudaState, expert_ids_per_pair: &CudaBuf, sorted_token_ids: &mut CudaBuf, block_ids: &mut CudaBuf,
+              total_tokens_post_pad: &mut CudaBuf, batch_x_topk: usize, num_experts: usize, block_size: usize,
+              sorted_max_size: usize, pair_ids: bool) -> Result<()> {
+    let stream = ctx.stream.clone();
+    let (e, _g0) = expert_ids_per_pair.as_i32().device_ptr(&stream);
+    let (s, _g1) = sorted_token_ids.as_i32_mut().device_ptr_mut(&stream);
+    let (b, _g2) = block_ids.as_i32_mut().device_ptr_mut(&stream);
+    let (t, _g3) = total_tokens_post_pad.as_i32_mut().device_ptr_mut(&stream);
+    unsafe {
+        fb2::moe::align_block_size(raw_stream(ctx), e as *const i32, s as *mut i32, b as *mut i32, t as *mut i32,
+                                   batch_x_topk, num_experts, block_size, sorted_max_size, pair_ids)
+    }
+    .map_err(|e| ferr("fb2 moe_align_block_size", e))
+}
+
+/// `moe_align_block_size` (capabilities.rs:389, CUDA impl moe.rs:358): sorted ids are token indices.
+#[allow(clippy::too_many_arguments)]
+pub fn moe_align_block_size(ctx: &mut CudaState, expert_ids_per_pair: &CudaBuf, sorted_token_ids: &mut CudaBuf,
+                            block_ids: &mut CudaBuf, total_tokens_post_pad: &mut CudaBuf, batch_x_topk: usize,
+                            num_experts: usize, block_size: usize, sorted_max_size: usize) -> Result<()> {
+    align_impl(ctx, expert_ids_per_pair, sorted_token_ids, block_ids, total_tokens_post_pad, batch_x_topk, num_experts,
+               block_size, sorted_max_size, false)
+}
+
+/// `moe_align_block_size_pair_ids` (capabilities.rs:406, CUDA impl moe.rs:420): sorted ids are pair indices.
+#[allow(clippy::too_many_arguments)]
+pub fn moe_align_block_size_pair_ids(ctx: &mut CudaState, expert_ids_per_pair: &CudaBuf, sorted_token_ids: &mut CudaBuf,
+                                     block_ids: &mut CudaBuf, total_tokens_post_pad: &mut CudaBuf, batch_x_topk: usize,
+                                     num_experts: usize, block_size: usize, sorted_max_size: usize) -> Result<()> {
+    align_impl(ctx, expert_ids_per_pair, sorted_token_ids, block_ids, total_tokens_post_pad, batch_x_topk, num_experts,
+               block_size, sorted_max_size, true)
+}
+
+/// `moe_combine` (capabilities.rs:683, CUDA impl moe.rs:476): no `Result` in the trait, a failed launch panics there too.
+#[allow(clippy::too_many_arguments)]
+pub fn moe_combine(ctx: &mut CudaState, packed_down: &CudaBuf, pairs_by_token: &CudaBuf, pair_weights: &CudaBuf,
+                   out: &mut CudaBuf, batch: usize, hidden: usize, top_k: usize, _total_pairs: usize) {
+    let stream = ctx.stream.clone();
+    let (d, _g0) = packed_down.as_f16().device_ptr(&stream);
+    let (p, _g1) = pairs_by_token.as_i32().device_ptr(&stream);
+    let (w, _g2) = pair_weights.as_f32().device_ptr(&stream);
+    let (o, _g3) = out.as_f16_mut().device_ptr_mut(&stream);
+    let rc = unsafe {
+        fb2::moe::combine(raw_stream(ctx), d as fb2::DevF16, p as *const i32, w as *const f32, o as fb2::DevF16Mut, batch,
+                          hidden, top_k)
+    };
+    if let Err(e) = rc {
+        panic!("fb2 moe_combine: {e}");
+    }
+}
+
+/// `weighted_sum_batched` (capabilities.rs:571, CUDA impl moe.rs:519).
+pub fn weighted_sum_batched(ctx: &mut CudaState, slots: &CudaBuf, weights: &CudaBuf, out: &mut CudaBuf, batch: usize,
+                            top_k: usize, hidden: usize) -> Result<()> {
+    let stream = ctx.stream.clone();
+    let (s, _g0) = slots.as_f16().device_ptr(&stream);
+    let (w, _g1) = weights.as_f32().device_ptr(&stream);
+    let (o, _g2) = out.as_f16_mut().device_ptr_mut(&stream);
+    unsafe {
+        fb2::moe::weighted_sum_batched(raw_stream(ctx), s as fb2::DevF16, w as *const f32, o as fb2::DevF16Mut, batch, top_k,
+                                       hidden)
+    }
+    .map_err(|e| ferr("fb2 weighted_sum_batched", e))
+}
+
+/// `fused_silu_mul_split` (Backend trait; CPU statement backend/cpu.rs:1666).
+pub fn fused_silu_mul_split(ctx: &mut CudaState, gate_up: &CudaBuf, out: &mut CudaBuf, tokens: usize, im: usize) {
+    let stream = ctx.stream.clone();
+    let (g, _g0) = gate_up.as_f16().device_ptr(&stream);
+    let (o, _g1) = out.as_f16_mut().device_ptr_mut(&stream);
+    let rc = unsafe { fb2::moe::fused_silu_mul_split(raw_stream(ctx), g as fb2::DevF16, o as fb2::DevF16Mut, tokens, im) };
+    if let Err(e) = rc {
+        panic!("fb2 fused_silu_mul_split: {e}");
+    }
+}
+
+// ------------------------------------------------------------------------------- collectives
+/// The shape of `NcclRank` (backend/cuda/nccl_comm.rs:8-56) over the library's communicator, one per
+/// rank process.  `tp_decode.rs:351-375` calls `all_reduce_f16_inplace` after each row-parallel GEMM;
+/// `forward_allreduce` below replaces that pair with the fused peer-memory kernel.
+pub struct Fb2NcclRank {
+    comm: fb2::Comm,
+    stream: Arc<cudarc::driver::CudaStream>,
+}
+unsafe impl Send for Fb2NcclRank {}
+unsafe impl Sync for Fb2NcclRank {}
+
+impl Fb2NcclRank {
+    /// Rank 0 creates the id (`fb2::Comm::unique_id`) and hands it to the other rank processes.
+    pub fn init_rank(id: &[u8; fb2::ffi::FB2_UNIQUE_ID_BYTES], rank: usize, world_size: usize, ordinal: usize,
+                     stream: Arc<cudarc::driver::CudaStream>) -> Result<Self> {
+        let comm = fb2::Comm::init_rank(id, rank as i32, world_size as i32, ordinal as i32).map_err(|e| ferr("fb2 comm init", e))?;
+        Ok(Self { comm, stream })
+    }
+    pub fn rank(&self) -> usize {
+        self.comm.rank()
+    }
+    pub fn world_size(&self) -> usize {
+        self.comm.world_size()
+    }
+    /// `NcclRank::all_reduce_f16_inplace` (nccl_comm.rs:40): sum over ranks, in place, on this rank's stream.
+    pub fn all_reduce_f16_inplace(&self, buf: &mut cudarc::driver::CudaSlice<half::f16>) -> Result<()> {
+        let len = buf.len();
+        let (p, _g) = buf.device_ptr_mut(&self.stream);
+        unsafe { self.comm.all_reduce_f16(self.stream.cu_stream() as *mut c_void, p as fb2::DevF16Mut, len) }
+            .map_err(|e| ferr("fb2 all_reduce", e))
+    }
+    /// Peer-memory receive slots for `forward_allreduce`; collective, outside graph capture.
+    pub fn enable_p2p(&mut self, max_elems: usize) -> Result<()> {
+        self.comm.enable_p2p(self.stream.cu_stream() as *mut c_void, max_elems).map_err(|e| ferr("fb2 enable_p2p", e))
+    }
+    /// Row-parallel GEMM + all-reduce in one call (the epilogue stores tiles into every peer's slot over NVLink).
+    pub fn forward_allreduce(&self, lin: &Fb2GptqLinear, input: &CudaBuf, out: &mut CudaBuf, m: usize) -> Result<()> {
+        let (x, _g0) = input.as_f16().device_ptr(&self.stream);
+        let (y, _g1) = out.as_f16_mut().device_ptr_mut(&self.stream);
+        unsafe {
+            lin.handle().forward_allreduce(&self.comm, self.stream.cu_stream() as *mut c_void, x as fb2::DevF16,
+                                           y as fb2::DevF16Mut, m)
+        }
+        .map_err(|e| ferr("fb2 forward_allreduce", e))
+    }
+}
