@@ -15,6 +15,17 @@
  * needs no CUDA include); routing indices are int32; combine weights are fp32.
  * There is no CPU fallback: every entry point that computes fails with
  * FB2_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Threads and streams.  Handles are immutable after create and may be shared between
+ * threads; create / destroy / pregrow calls are serialised inside the library; the error
+ * message is thread-local.  Launches on one device share that device's scratch (split-K
+ * partials, fix-up slots, the act-order gather buffer), exactly as the reference's Marlin
+ * path shares its gather scratch and workspace per device (quant.rs:228-322): work
+ * submitted through this library to ONE device must be ordered on ONE stream at a time
+ * (or on streams the caller orders with events).  Different devices are independent.
+ * The `*_forward_host*` calls run on a private stream, return after synchronising it and
+ * serialise themselves with a mutex; do not overlap them with other work of this library
+ * on the same device.
  */
 #ifndef FB2_W4A16_H
 #define FB2_W4A16_H
