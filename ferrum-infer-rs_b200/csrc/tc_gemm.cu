@@ -143,6 +143,20 @@ static_assert((size_t)kLlMaxCtas * kLlFloatsPerCta * sizeof(uint32_t) == kLlByte
 // registers (k0,k1) (k2,k3) (k4,k5) (k6,k7).
 __device__ __forceinline__ void dequant_word(uint32_t q, __half2 zlo, __half2 zhi, __half2 s2,
                                              uint32_t *out) {
+#ifdef FB2_EXP_RAW_NIBBLES
+  // Timing probe for the round-2 plan ("Next (a)"): the nibbles go to the tensor core as fp16
+  // SUBNORMALS (q * 2^-24 from bits 3:0, q * 2^-20 from bits 7:4 of each half) -- 5 instructions a word instead of
+  // 13 -- and scale / zero point would move to the accumulator side.  That side is not written yet, so a build
+  // with this macro is NUMERICALLY WRONG on purpose; it is never defined in the product build and exists to time
+  // the dequant loop (scripts/build_variant.sh rawnib "-DFB2_EXP_RAW_NIBBLES", FB2_LIB=..., scripts/shape_sweep.py).
+  (void)zlo; (void)zhi; (void)s2;
+  const uint32_t q2r = q >> 8;
+  out[0] = q & 0x000f000fu;
+  out[1] = q & 0x00f000f0u;
+  out[2] = q2r & 0x000f000fu;
+  out[3] = q2r & 0x00f000f0u;
+  return;
+#endif
   const uint32_t kMagic = 0x64006400u;                 // half2(1024, 1024)
   const __half2 k16th = __float2half2_rn(0.0625f);
   uint32_t lo0 = ptx::lop3_and_or(q, 0x000f000fu, kMagic);   // 1024 + q      (k0,k1)
