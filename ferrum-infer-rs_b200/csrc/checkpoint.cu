@@ -104,11 +104,15 @@ struct JsonParser {
           case 'u': {
             unsigned cp;
             if (!hex4(cp)) return false;
-            if (cp >= 0xD800 && cp < 0xDC00 && end - p >= 6 && p[0] == '\\' && p[1] == 'u') {
+            if (cp >= 0xD800 && cp < 0xDC00) {          // high surrogate: a low one must follow (serde_json rejects lone ones)
+              if (end - p < 6 || p[0] != '\\' || p[1] != 'u') return fail("lone surrogate in \\u escape");
               p += 2;
               unsigned lo;
               if (!hex4(lo)) return false;
+              if (lo < 0xDC00 || lo > 0xDFFF) return fail("bad surrogate pair in \\u escape");
               cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+            } else if (cp >= 0xDC00 && cp <= 0xDFFF) {
+              return fail("lone surrogate in \\u escape");
             }
             put_utf8(out, cp);
             break;
@@ -116,11 +120,35 @@ struct JsonParser {
           default: return fail("bad escape");
         }
       } else {
+        if ((unsigned char)*p < 0x20) return fail("control character in string");
         out += *p++;
       }
     }
     if (p >= end) return fail("unterminated string");
     p++;
+    if (!valid_utf8(out)) return fail("string is not valid UTF-8");
+    return true;
+  }
+  // RFC 3629: no overlong forms, no surrogates, nothing above U+10FFFF (what serde_json enforces on the reference side)
+  static bool valid_utf8(const std::string &s) {
+    const unsigned char *q = (const unsigned char *)s.data(), *e = q + s.size();
+    while (q < e) {
+      const unsigned c = *q;
+      int n;
+      unsigned cp, lo;
+      if (c < 0x80) { q++; continue; }
+      else if ((c & 0xE0) == 0xC0) { n = 1; cp = c & 0x1F; lo = 0x80; }
+      else if ((c & 0xF0) == 0xE0) { n = 2; cp = c & 0x0F; lo = 0x800; }
+      else if ((c & 0xF8) == 0xF0) { n = 3; cp = c & 0x07; lo = 0x10000; }
+      else return false;
+      if (e - q <= n) return false;
+      for (int i = 1; i <= n; i++) {
+        if ((q[i] & 0xC0) != 0x80) return false;
+        cp = (cp << 6) | (q[i] & 0x3F);
+      }
+      if (cp < lo || cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return false;
+      q += n + 1;
+    }
     return true;
   }
   bool value(Json &v) {

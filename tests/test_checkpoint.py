@@ -364,3 +364,35 @@ def test_header_json_corner_cases(fb2, tmp_path):
         with pytest.raises(fb2.Fb2Error) as e:
             fb2.NativeSafetensorsLoader.open(tmp_path)
         assert e.value.code == -6
+
+
+def test_header_strings_are_strict_json(fb2, tmp_path):
+    """The reference parses headers with serde_json, which rejects invalid UTF-8, raw control characters and lone
+    surrogates; so does this parser (a tensor name is handed back to the caller as a C string)."""
+    entry = b'{"dtype": "F32", "shape": [1], "data_offsets": [0, 4]}'
+    bad_names = [b'"t\xed\xa0\x80"',          # UTF-8-encoded surrogate
+                 b'"t\xff"', b'"t\xc3"',      # invalid lead byte, truncated sequence
+                 b'"t\xc0\xaf"',              # overlong '/'
+                 b'"t\xf4\x90\x80\x80"',      # above U+10FFFF
+                 b'"t\x01"', b'"t\nx"',       # raw control characters
+                 b'"\\ud800"', b'"\\udc00"', b'"\\ud800\\u0041"']   # lone / mismatched surrogates
+    for nm in bad_names:
+        hj = b"{" + nm + b": " + entry + b"}"
+        (tmp_path / "model.safetensors").write_bytes(struct.pack("<Q", len(hj)) + hj + b"\0" * 8)
+        with pytest.raises(fb2.Fb2Error) as e:
+            fb2.NativeSafetensorsLoader.open(tmp_path)
+        assert e.value.code == -6, nm
+    good = '{"\\ud83d\\ude00 é\\u00e9": '.encode("utf-8") + entry + b"}"
+    (tmp_path / "model.safetensors").write_bytes(struct.pack("<Q", len(good)) + good + b"\0" * 8)
+    assert fb2.NativeSafetensorsLoader.open(tmp_path).tensor_names() == ["\U0001F600 éé"]
+
+
+def test_fuzzed_containers_never_crash_the_parser():
+    """scripts/fuzz_checkpoint.py: 300 mutated containers / config files / shard indices are each either loaded or
+    rejected with a status; a crash of the C++ ingest kills the child process and fails here."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_checkpoint.py"), "300", "11"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "no crash" in out.stdout, (out.returncode, out.stdout[-500:], out.stderr[-2000:])
