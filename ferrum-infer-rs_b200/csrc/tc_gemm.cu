@@ -157,6 +157,33 @@ __device__ __forceinline__ void dequant_word(uint32_t q, __half2 zlo, __half2 zh
   out[3] = q2r & 0x00f000f0u;
   return;
 #endif
+#ifdef FB2_EXP_NO_ZERO
+  // Second timing probe: f16_rn(q * s) with ONE fma per half2 -- fma(1024 + q, s, -1024 s) and
+  // fma(1024 + 16 q, s / 16, -64 s), both constants exact -- 9 instructions a word; the zero term -z s Sum(x) would go
+  // through one extra MMA k-step per unit.  That k-step is not written yet: NUMERICALLY WRONG on purpose, never in the
+  // product build.
+  (void)zlo; (void)zhi;
+  {
+    const uint32_t kMagicP = 0x64006400u;
+    const __half2 s16 = __hmul2(s2, __float2half2_rn(0.0625f));
+    const __half2 c_lo = __hmul2(s2, __float2half2_rn(-1024.0f));
+    const __half2 c_hi = __hmul2(s2, __float2half2_rn(-64.0f));
+    uint32_t a0 = ptx::lop3_and_or(q, 0x000f000fu, kMagicP);
+    uint32_t b0 = ptx::lop3_and_or(q, 0x00f000f0u, kMagicP);
+    const uint32_t qq = q >> 8;
+    uint32_t a1 = ptx::lop3_and_or(qq, 0x000f000fu, kMagicP);
+    uint32_t b1 = ptx::lop3_and_or(qq, 0x00f000f0u, kMagicP);
+    __half2 w0 = __hfma2(*reinterpret_cast<__half2 *>(&a0), s2, c_lo);
+    __half2 w1 = __hfma2(*reinterpret_cast<__half2 *>(&b0), s16, c_hi);
+    __half2 w2 = __hfma2(*reinterpret_cast<__half2 *>(&a1), s2, c_lo);
+    __half2 w3 = __hfma2(*reinterpret_cast<__half2 *>(&b1), s16, c_hi);
+    out[0] = *reinterpret_cast<uint32_t *>(&w0);
+    out[1] = *reinterpret_cast<uint32_t *>(&w1);
+    out[2] = *reinterpret_cast<uint32_t *>(&w2);
+    out[3] = *reinterpret_cast<uint32_t *>(&w3);
+    return;
+  }
+#endif
   const uint32_t kMagic = 0x64006400u;                 // half2(1024, 1024)
   const __half2 k16th = __float2half2_rn(0.0625f);
   uint32_t lo0 = ptx::lop3_and_or(q, 0x000f000fu, kMagic);   // 1024 + q      (k0,k1)

@@ -1,7 +1,9 @@
-"""Round-2 probe, to be run on a B200 with the probe build of the library:
+"""Round-2 probes, to be run on a B200 with a probe build of the library:
 
-    scripts/build_variant.sh rawnib "-DFB2_EXP_RAW_NIBBLES"
+    scripts/build_variant.sh rawnib "-DFB2_EXP_RAW_NIBBLES"      # 78 instructions per unit
+    scripts/build_variant.sh nozero "-DFB2_EXP_NO_ZERO"          # 116 instructions per unit
     FB2_LIB=$PWD/ferrum-infer-rs_b200/csrc/build/variants/rawnib.so python scripts/rawnib_probe.py
+    FB2_LIB=$PWD/ferrum-infer-rs_b200/csrc/build/variants/nozero.so python scripts/rawnib_probe.py
 
 Answers two questions before the accumulator-side scale / zero epilogue is written ("Next (a)"):
  1. does tcgen05.mma kind::f16 honour fp16 SUBNORMAL A operands (q * 2^-24, q * 2^-20)?  The probe build writes the raw
@@ -20,7 +22,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 
 fb2 = importlib.import_module("ferrum-infer-rs_b200")
-assert "rawnib" in os.environ.get("FB2_LIB", ""), "run with FB2_LIB pointing at the rawnib variant"
+variant = os.environ.get("FB2_LIB", "")
+assert "rawnib" in variant or "nozero" in variant, "run with FB2_LIB pointing at the rawnib or the nozero variant"
 
 rng = np.random.default_rng(1)
 k, n, m = 512, 256, 1
@@ -30,11 +33,19 @@ x = rng.uniform(-1, 1, size=(m, k)).astype(np.float16)
 y = lin.forward(torch.from_numpy(x).cuda()).float().cpu().numpy()
 kk = np.arange(k)
 q = ((qw.view(np.uint32)[kk // 8, :] >> ((kk % 8) * 4).astype(np.uint32)[:, None]) & 0xF).astype(np.float64)   # [k, n]
-c = np.where(np.isin(kk % 8, (0, 1, 4, 5)), 2.0 ** -24, 2.0 ** -20)
-want = (x.astype(np.float64) * c[None, :]) @ q
-err = np.abs(y - want).max() / np.abs(want).max()
-print(f"subnormal A operand: max|y|={np.abs(y).max():.3e} expected {np.abs(want).max():.3e} rel err {err:.2e} ->",
-      "HONOURED" if err < 2e-3 else ("FLUSHED TO ZERO" if np.abs(y).max() == 0 else "MISMATCH (check the k order assumed here)"))
+if "rawnib" in variant:
+    c = np.where(np.isin(kk % 8, (0, 1, 4, 5)), 2.0 ** -24, 2.0 ** -20)
+    want = (x.astype(np.float64) * c[None, :]) @ q
+    err = np.abs(y - want).max() / np.abs(want).max()
+    print(f"subnormal A operand: max|y|={np.abs(y).max():.3e} expected {np.abs(want).max():.3e} rel err {err:.2e} ->",
+          "HONOURED" if err < 2e-3 else ("FLUSHED TO ZERO" if np.abs(y).max() == 0 else "MISMATCH (check the k order assumed here)"))
+else:
+    # nozero build: the A operand is f16_rn(q * s) (one fma, exact constants); the zero term is missing on purpose
+    s_kn = np.repeat(np.asarray(sc, np.float32).reshape(k // 128, n), 128, axis=0)
+    w = (q.astype(np.float32) * s_kn).astype(np.float16).astype(np.float64)
+    want = x.astype(np.float64) @ w
+    err = np.abs(y - want).max() / np.abs(want).max()
+    print(f"q*s operand: rel err {err:.2e} ->", "AS DESIGNED" if err < 2e-3 else "MISMATCH")
 
 out = {}
 for (name, kk_, nn_) in bench.LLAMA["linears"]:
