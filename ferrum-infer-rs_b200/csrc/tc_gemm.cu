@@ -47,6 +47,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "rowmap.cuh"
+#include "sched.cuh"
 
 namespace fb2 {
 
@@ -245,58 +246,8 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, float *v) {
   }
 }
 
-// ---- stream-K bookkeeping (identical in every role) -------------------------------------
-// All of it is 32-bit unsigned arithmetic: the host keeps (units x CTAs) below 2^31 (launch_tc_gemm cuts
-// larger dense batches into several launches).  The emulated 64-bit divisions this replaces sat on the
-// critical path twice: before the first weight request of every CTA and in front of every fix-up.
-typedef unsigned int u32;
-__device__ __forceinline__ u32 range_start(u32 c, u32 T, u32 G) { return c * T / G; }
-// Tiles of only a few units (K <= 1024: the MoE down projection has 6) are never split: cutting one
-// costs a partial-tile fix-up (~3 us) that is longer than streaming the whole tile.  CTA c then owns
-// the whole tiles [c * NT / G, (c + 1) * NT / G) -- when that balances: at most one tile per CTA, or so
-// many that a difference of one tile is small (measured on the Qwen3 MoE down projection).
-constexpr int kWholeTileMaxUnits = 8;
-__host__ __device__ __forceinline__ bool whole_tile_mode(int upt, long long n_tiles_total, int slots) {
-  return upt <= kWholeTileMaxUnits && (n_tiles_total <= slots || n_tiles_total >= 4LL * slots);
-}
-__device__ __forceinline__ u32 tile_range_start(u32 c, u32 NT, u32 G, u32 upt) { return (c * NT / G) * upt; }
-__device__ __forceinline__ int cta_of_unit(u32 u, u32 T, u32 G) {
-  u32 c = u * G / T;
-  while (c + 1 < G && range_start(c + 1, T, G) <= u) c++;
-  while (c > 0 && range_start(c, T, G) > u) c--;
-  return (int)c;
-}
-
-// One CTA's unit range, cut into SEGMENTS: maximal runs of units that belong to one output
-// tile (row block, tile).  r0/r1 index the tile's unit list [gate groups..., up groups...].
-struct Seg {
-  int blk, tile, r0, r1;
-  int at_start;              // the segment starts at the CTA's range start (partial slot 0)
-};
-struct SegIter {
-  int blk, tile, r, left, first;
-  __device__ __forceinline__ void init(u32 u0, u32 u1, int upt, int n_tiles) {
-    const u32 tau = u0 / (u32)upt;
-    r = (int)(u0 - tau * (u32)upt);
-    blk = (int)(tau / (u32)n_tiles);
-    tile = (int)(tau - (u32)blk * (u32)n_tiles);
-    left = (int)(u1 - u0);
-    first = 1;
-  }
-  __device__ __forceinline__ bool next(Seg &s, int upt, int n_tiles) {
-    if (left <= 0) return false;
-    const int n = min(left, upt - r);
-    s.blk = blk; s.tile = tile; s.r0 = r; s.r1 = r + n; s.at_start = first;
-    first = 0;
-    left -= n;
-    r += n;
-    if (r == upt) {
-      r = 0;
-      if (++tile == n_tiles) { tile = 0; blk++; }
-    }
-    return true;
-  }
-};
+// stream-K bookkeeping (range_start, whole_tile_mode, tile_range_start, cta_of_unit, Seg, SegIter): sched.cuh
+using namespace sched;
 
 // ring position: stage index + phase parity, advanced without division
 struct RingPos {
@@ -1044,21 +995,10 @@ TcPlan make_plan(const WeightRef &w, const RowMap &rows, int epilogue, int sm_co
   const int per_sm = ctas_per_sm_dbg ? ctas_per_sm_dbg : (pl.nb >= 128 ? 1 : 2);
   const int slots = per_sm * (sm_count > 0 ? sm_count : 148);
   const int upt = pl.nacc * (w.k / kGroup);
-  pl.whole_tiles = rows.mode != ROWS_ROUTED && whole_tile_mode(upt, units / upt, slots);
-  long long g = pl.whole_tiles ? units / upt : units / 2;         // whole tiles | >= 2 units per CTA
-  if (g < 1) g = 1;
-  pl.grid = (int)(g < slots ? g : slots);
-  // Few tiles (decode qkv / o / down: 32-48 of them): give every tile the same whole number s of
-  // CTAs.  With G = tiles * s the ranges c*T/G fall on tile boundaries, so no CTA straddles two tiles
-  // (a straddling CTA pays a mid-stream epilogue AND owns the next tile's fix-up: it was the
-  // straggler of these launches in the in-kernel timeline).
   static const bool no_align = [] { const char *e = getenv("FB2_DEBUG_NO_TILE_ALIGN"); return e && e[0] == '1'; }();
-  const long long nt = units / upt;
-  if (!no_align && !pl.whole_tiles && rows.mode != ROWS_ROUTED && nt > 0 && nt * 2 <= slots) {
-    long long s = slots / nt;
-    if (s > upt / 2) s = upt / 2;                                   // >= 2 units per CTA
-    if (s >= 1) pl.grid = (int)(nt * s);
-  }
+  const GridPlan gp = plan_grid(units, upt, slots, rows.mode == ROWS_ROUTED, !no_align);   // sched.cuh
+  pl.whole_tiles = gp.whole_tiles;
+  pl.grid = gp.grid;
   pl.partial_floats = (size_t)pl.grid * pl.nacc * pl.nb * kTileN;
   pl.counters = (size_t)pl.row_blocks * pl.n_tiles;
   pl.smem = pl.nb == 16 ? smem_of<16>() : pl.nb == 32 ? smem_of<32>() : pl.nb == 64 ? smem_of<64>()
