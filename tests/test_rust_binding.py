@@ -127,3 +127,17 @@ def test_rust_sources_are_bracket_balanced(path):
         elif c in pairs:
             assert stack and stack.pop() == pairs[c], f"unbalanced '{c}' in {path}"
     assert not stack
+
+
+def test_integration_md_excerpts_match_the_declarations():
+    """The `extern "C"` excerpts in INTEGRATION.md are for reading; they must still name declared functions with the
+    declared number of arguments."""
+    decls = _ffi_decls()
+    src = _strip(open(os.path.join(ROOT, "INTEGRATION.md")).read())
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    seen = 0
+    for m in re.finditer(r"pub fn (fb2_\w+)\(", src):
+        assert m.group(1) in decls, m.group(1)
+        assert len(_args_at(src, m.end() - 1)) == decls[m.group(1)], m.group(1)
+        seen += 1
+    assert seen >= 20
