@@ -307,3 +307,19 @@ def test_committed_golden_vectors(oracle):
         x = oracle.f16_round(oracle.lcg_f32_array(0xC0FFEE, m * k, -1.0, 1.0))
         y = oracle.linear_forward(x, w, None, m)
         assert np.array_equal(y.view(np.uint32), z[f"{tag}_y"].view(np.uint32))
+
+
+def test_full_size_anchor_and_llama_down_against_numpy(oracle):
+    """BASELINE.json configs[0] (K = N = 4096, g = 128, M = 1, act-order) and the Llama-3.1-8B down projection
+    (K = 14336, N = 4096, M = 2) at FULL size: the C oracle's dequant equals the independent numpy restatement bit for
+    bit, and its f64-accumulate GEMM (cpu.rs:481-492) equals numpy's float64 product rounded to f32 within one ulp."""
+    for (k, n, m, seed) in [(4096, 4096, 1, 0xA11C), (14336, 4096, 2, 0xD0)]:
+        syn = oracle.make_synthetic(k, n, 128, seed, f16_scales=True)
+        gi = oracle.random_balanced_g_idx(k, 128, seed & 0xFFFF)
+        w = oracle.dequant_gptq(syn.qweight, syn.scales, syn.qzeros, gi, 4, 128, k, n)
+        assert np.array_equal(w.view(np.uint32), oracle.np_dequant_gptq(syn.qweight, syn.scales, syn.qzeros, gi, 128, k, n).view(np.uint32))
+        x = oracle.f16_round(oracle.lcg_f32_array(0xC0FFEE, m * k, -1.0, 1.0)).reshape(m, k)
+        got = oracle.linear_forward(x, w, None, m, threads=8)
+        ref = (x.astype(np.float64) @ w.astype(np.float64).T)
+        # numpy's pairwise / blocked f64 summation differs from the sequential one by a few f64 ulps: far below f32's
+        assert np.all(np.abs(got.astype(np.float64) - ref) <= np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64))
