@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FFI_RS = os.path.join(ROOT, "rust", "fb2-w4a16-sys", "src", "ffi.rs")
 LIB_RS = os.path.join(ROOT, "rust", "fb2-w4a16-sys", "src", "lib.rs")
 FERRUM_RS = os.path.join(ROOT, "rust", "ferrum-kernels", "src", "quant_linear", "fb2_w4a16.rs")
+EXAMPLE_RS = os.path.join(ROOT, "rust", "fb2-w4a16-sys", "examples", "cuda_vs_cpu.rs")
 HEADER = os.path.join(ROOT, "include", "fb2_w4a16.h")
 SO = os.path.join(ROOT, "ferrum-infer-rs_b200", "libfb2_w4a16.so")
 
@@ -117,7 +118,7 @@ def test_ferrum_drop_in_calls_match_the_wrapper():
         assert re.search(rf"\b{variant}\(String\)", open(LIB_RS).read()), variant
 
 
-@pytest.mark.parametrize("path", [FFI_RS, LIB_RS, FERRUM_RS])
+@pytest.mark.parametrize("path", [FFI_RS, LIB_RS, FERRUM_RS, EXAMPLE_RS])
 def test_rust_sources_are_bracket_balanced(path):
     src = _strip(open(path).read())
     stack, pairs = [], {")": "(", "]": "[", "}": "{"}
@@ -141,3 +142,12 @@ def test_integration_md_excerpts_match_the_declarations():
         assert len(_args_at(src, m.end() - 1)) == decls[m.group(1)], m.group(1)
         seen += 1
     assert seen >= 20
+
+
+def test_example_calls_match_the_wrapper():
+    """rust/fb2-w4a16-sys/examples/cuda_vs_cpu.rs (the reference's cuda_vs_cpu fixture driven from Rust)."""
+    fns = _wrapper_fns()
+    src = _strip(open(EXAMPLE_RS).read())
+    for name, call in (("load_gptq", "GptqLinear::load_gptq("), ("forward_host", "lin.forward_host(")):
+        i = src.index(call) + len(call) - 1
+        assert len(_args_at(src, i)) in fns[name], name
