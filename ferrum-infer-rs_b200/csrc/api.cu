@@ -147,8 +147,7 @@ static TcScratch current_scratch(int device, int *sm_count) {
 
 // -------------------------------------------------------------------- repack kernels
 // Raw GPTQ tensors (device copies of what load_gptq receives) -> tile-stripe format.
-// One thread per output word; with perm == nullptr all 8 nibbles of an output word come
-// from ONE source word (a nibble shuffle), with act-order they are 8 gathers.
+// One thread per output word: 8 nibble gathers (tile_nibble_k gives the sorted k of each nibble).
 __global__ void repack_tiles_kernel(const int32_t *__restrict__ qweight,   // [K/8][n]
                                     const float *__restrict__ scales,      // [G][n]
                                     const int32_t *__restrict__ qzeros,    // [G][n/8]
@@ -174,23 +173,13 @@ __global__ void repack_tiles_kernel(const int32_t *__restrict__ qweight,   // [K
   }
   const int j = word & 3, nl = (word >> 2) & 127, c = word >> 9;
   const int col = t * kTileN + nl;
-  const int sk0 = g * kGroup + c * kChunkK + j * 8;
   uint32_t out = 0;
-  if (perm == nullptr) {
-    const uint32_t src = (uint32_t)qweight[(size_t)(sk0 >> 3) * n + col];
 #pragma unroll
-    for (int p = 0; p < 8; p++) {
-      const int koff = p < 4 ? 2 * p : 2 * (p - 4) + 1;
-      out |= ((src >> (koff * 4)) & 0xFu) << (p * 4);
-    }
-  } else {
-#pragma unroll
-    for (int p = 0; p < 8; p++) {
-      const int koff = p < 4 ? 2 * p : 2 * (p - 4) + 1;
-      const int dk = perm[sk0 + koff];
-      const uint32_t src = (uint32_t)qweight[(size_t)(dk >> 3) * n + col];
-      out |= ((src >> ((dk & 7) * 4)) & 0xFu) << (p * 4);
-    }
+  for (int p = 0; p < 8; p++) {
+    const int sk = g * kGroup + tile_nibble_k(c, j, p);          // sorted k of this nibble
+    const int dk = perm ? perm[sk] : sk;                          // disk row
+    const uint32_t src = (uint32_t)qweight[(size_t)(dk >> 3) * n + col];
+    out |= ((src >> ((dk & 7) * 4)) & 0xFu) << (p * 4);
   }
   stage[word] = out;
 }

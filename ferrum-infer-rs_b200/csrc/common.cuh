@@ -47,8 +47,13 @@ bool pdl_enabled();
 // ------------------------------------------------------------------ tiled weight format
 // The "tile stripe" layout the tensor-core kernels stream (data layout):
 //   for each 128-column tile t, for each 128-row group g (rows in act-order-SORTED k):
-//     8192 B  packed int4: 4 chunks of 32 k; chunk c = 128 rows(n) x uint4; word j of the
-//             uint4 holds k = 32c + 8j + {0,2,4,6,1,3,5,7} in nibbles 0..7
+//     8192 B  packed int4: 4 chunks of 16 B per column; chunk c = 128 columns(n) x uint4.  A dequant thread
+//             (column n, 64-k half h) reads chunks 2h, 2h+1 = words J = 0..7; nibble p of word J holds
+//             k = 64h + 32 (p & 1) + 4J + {0,2,1,3}[p >> 1]  (tile_nibble_k below): even nibbles ("lo class",
+//             bits 3:0 / 19:16 after an optional shift by 8) fill MMA k-steps 0,1 of the half, odd nibbles
+//             ("hi class", bits 7:4 / 23:20) k-steps 2,3 -- so `w & 0x000f000f` and `w & 0x00f000f0` are
+//             half2 pairs of consecutive k, and every k-step of the UMMA A operand is class-pure (the decode
+//             kernel feeds the raw nibbles to the tensor core as fp16 subnormals, q * 2^-24 / q * 2^-20).
 //      512 B  128 x u32: lo half = f16 scale, hi half = f16 (1024 + zero)
 constexpr int kTileN = 128;          // weight columns per tile  (UMMA M)
 constexpr int kGroup = 128;          // k rows per stage == GPTQ group_size of the fast path
@@ -56,6 +61,11 @@ constexpr int kChunkK = 32;          // k per uint4
 constexpr int kStageWBytes = kTileN * kGroup / 2;           // 8192
 constexpr int kStageSZBytes = kTileN * 4;                   // 512
 constexpr int kStageBytes = kStageWBytes + kStageSZBytes;   // 8704
+// k offset inside the group of nibble p (0..7) of word j (0..3) of chunk c (0..3)
+__host__ __device__ __forceinline__ int tile_nibble_k(int c, int j, int p) {
+  const int h = c >> 1, J = (c & 1) * 4 + j;
+  return 64 * h + 32 * (p & 1) + 4 * J + ((p >> 1) & 1) * 2 + (p >> 2);
+}
 
 // ------------------------------------------------------------------------ row-block map
 // Every GEMM kernel works on "row blocks": up to NB activation rows that share one weight

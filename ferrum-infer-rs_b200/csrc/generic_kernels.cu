@@ -205,8 +205,7 @@ __global__ void dequant_tiled_kernel(const WeightRef w, int expert, OutT *__rest
   const int col = t * kTileN + nl;
 #pragma unroll
   for (int p = 0; p < 8; p++) {
-    const int koff = p < 4 ? 2 * p : 2 * (p - 4) + 1;
-    const int sk = g * kGroup + c * kChunkK + j * 8 + koff;
+    const int sk = g * kGroup + tile_nibble_k(c, j, p);
     const int dk = w.perm ? w.perm[sk] : sk;
     store_w<OutT>(out + (size_t)col * w.k + dk, (float)((int)((packed >> (p * 4)) & 0xF) - z) * s);
   }

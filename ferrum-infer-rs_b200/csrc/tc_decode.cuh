@@ -1,0 +1,506 @@
+// tc_decode.cuh -- the decode-batch (<= 16 rows per block) form of the tensor-core W4A16 kernel.  Included by
+// tc_gemm.cu (same translation unit: it shares TcParams, the stream-K bookkeeping and the launch helpers).
+//
+// What differs from tc_body (tc_gemm.cu):
+//   * RAW NIBBLES.  The int4 weights go to the tensor core UNSCALED, as fp16 subnormals: `w & 0x000f000f` is the
+//     half2 (q, q') * 2^-24, `w & 0x00f000f0` is (q, q') * 2^-20 -- 5 integer instructions per packed word
+//     instead of 13 (tcgen05.mma kind::f16 honours subnormal operands: measured, scripts/rawnib_probe.py in
+//     round 2).  The tile format keeps every MMA k-step class-pure (common.cuh, tile_nibble_k); the four hi-class
+//     k-steps of a unit are issued first and the first lo-class MMA carries scale-input-d = 4
+//     (D = A.B + D * 2^-4), so one accumulator holds 2^-24 * sum_k q_k x_k exactly.
+//   * SCALE AND ZERO POINT ON THE ACCUMULATOR SIDE.  Every unit (one 128 x 128 stage) gets a FRESH accumulator
+//     D[slot] and a second one, D2[slot] = ones . x^T = sum_k x_k of the group (eight more MMAs against a constant
+//     all-ones A operand of 8 TMEM columns).  The dequant warps read both back (tcgen05.ld, R columns = real rows)
+//     and keep the running sum in REGISTERS: acc[r] += (s 2^24) D[r] - (s z) D2[r], two fp32 FMAs per row and unit
+//     instead of three fp16 instructions per weight pair.  The weight is never rounded to fp16: results are closer
+//     to the f64 reference than the prefill path's.
+//   * TWO UNITS IN FLIGHT PER CTA.  The eight dequant warps form two groups of four (one warp per TMEM lane
+//     quarter, all 128 k of the unit); group s owns A slot s / D[s] / D2[s] and takes every second unit.  A unit
+//     costs each warp two barrier waits instead of the old five, and while one group waits for its MMAs the other
+//     converts -- the old loop was bound by that per-unit latency chain, not by instruction issue (halving its
+//     instruction count bought 13 %).
+//   * The accumulators live in registers, so the MMA warp knows nothing about tiles or segments, and the epilogue
+//     starts from registers: the two groups swap the rows the other one finishes through shared memory, then run
+//     the same whole-tile / flag-in-value / counter exchange as tc_body.
+#pragma once
+
+namespace dk {
+
+constexpr int kNB = 16;                     // UMMA N: rows of a block (<= 16 real)
+constexpr int kXSlots = 4;
+constexpr int kXBytes = kNB * 256;          // [2 atoms][16 rows][128 B]
+constexpr int kXchgBytes = 16 * kTileN * 4; // group <-> group exchange of partial sums
+constexpr int kSmemBudget = 108 * 1024;
+constexpr int kWBase = kXSlots * kXBytes;   // 1024-aligned
+constexpr int kWStages = (kSmemBudget - 1024 - kWBase - kXchgBytes) / kStageBytes;      // 9
+constexpr int kXchgBase = kWBase + kWStages * kStageBytes;
+constexpr int kBarBase = (kXchgBase + kXchgBytes + 127) & ~127;
+constexpr int kSmemBytes = kBarBase + 1024;
+static_assert(kWStages >= 4 && kWStages <= kMaxWStages, "weight ring depth");
+// tensor memory columns (256 allocated): A slots, per-slot accumulators, the constant ones operand
+constexpr int kTmemCols = 256;
+constexpr int kColA = 0;                    // 2 slots x 64
+constexpr int kColD = 128;                  // 2 x 16: sum_k q_k x_k * 2^-24
+constexpr int kColD2 = 160;                 // 2 x 16: sum_k x_k
+constexpr int kColOnes = 192;               // 8 columns of half2(1, 1)
+enum { BAR_FULL_W = 0, BAR_EMPTY_W = kMaxWStages, BAR_FULL_X = 2 * kMaxWStages, BAR_EMPTY_X = BAR_FULL_X + kXSlots,
+       BAR_FULL_A = BAR_EMPTY_X + kXSlots, BAR_DONE = BAR_FULL_A + 2, BAR_COUNT = BAR_DONE + 2 };
+static_assert(BAR_COUNT * 8 <= 512, "barrier area too small");
+
+template <int R>
+__device__ __forceinline__ void tmem_ld_rows(uint32_t taddr, uint32_t (&r)[R]) {
+  if constexpr (R == 1) ptx::tmem_ld_x1(taddr, r);
+  else if constexpr (R == 2) ptx::tmem_ld_x2(taddr, r);
+  else if constexpr (R == 4) ptx::tmem_ld_x4(taddr, r);
+  else if constexpr (R == 8) ptx::tmem_ld_x8(taddr, r);
+  else ptx::tmem_ld_x16(taddr, r);
+}
+
+// R = accumulator columns each dequant thread reads per unit: the real rows of a block rounded up to a power of two.
+template <int R, bool kPush>
+__device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "rows per thread");
+  constexpr int SW = kWStages, SX = kXSlots;
+  constexpr int OWN = R <= 4 ? R : R / 2;           // rows a group finishes in the epilogue (group 1: none when R <= 4)
+  constexpr int kEpiThreads = R <= 4 ? 128 : 256;   // threads that take part in the inter-CTA exchange
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = (int)gridDim.x;
+  const int cta = (int)blockIdx.x;
+  const int groups = p.groups, n_tiles = p.n_tiles;
+  const int upt = groups;                                        // units per output tile
+  const u32 T = (u32)rowmap_num_blocks(p.rm, kNB) * (u32)n_tiles * (u32)upt;
+  u32 u0, u1;
+  if (p.whole_tiles) {
+    u0 = tile_range_start(cta, T / upt, G, upt);
+    u1 = tile_range_start(cta + 1, T / upt, G, upt);
+  } else {
+    u0 = range_start(cta, T, G);
+    u1 = range_start(cta + 1, T, G);
+  }
+  if (u0 >= u1) return;                                          // CTA-uniform, before any barrier
+
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t bars = smem_base + kBarBase;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kBarBase + 512);
+  const size_t tile_stride = (size_t)groups * kStageBytes;
+
+  // ------------------------------------------------------------------ one-time setup
+  if (warp == kWarpW) {
+    if (lane == 0) {
+      for (int i = 0; i < SW; i++) {
+        ptx::mbar_init(bar(BAR_FULL_W + i), 1);                  // the producer's arrive.expect_tx
+        ptx::mbar_init(bar(BAR_EMPTY_W + i), 4);                 // read into registers by the 4 warps of one group
+      }
+      ptx::mbar_fence_init();
+    }
+    __syncwarp();
+    ptx::named_bar_arrive(2, kThreads);
+  } else if (warp == kWarpX) {
+    if (lane == 0) {
+      for (int i = 0; i < SX; i++) {
+        ptx::mbar_init(bar(BAR_FULL_X + i), 1);
+        ptx::mbar_init(bar(BAR_EMPTY_X + i), 1);                 // the MMA commit
+      }
+      ptx::mbar_fence_init();
+    }
+    __syncwarp();
+    ptx::named_bar_arrive(2, kThreads);
+  } else if (warp == kWarpMma) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; i++) {
+        ptx::mbar_init(bar(BAR_FULL_A + i), 4);
+        ptx::mbar_init(bar(BAR_DONE + i), 1);
+      }
+      ptx::mbar_fence_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(s_tmem));
+  }
+  uint32_t tmem_base = 0;
+  if (warp != kWarpW && warp != kWarpX) {
+    ptx::tc_fence_before();
+    ptx::named_bar_sync(2, kThreads);
+    ptx::tc_fence_after();
+    tmem_base = *s_tmem;
+  }
+  const u32 n_units = u1 - u0;
+
+  if (warp == kWarpW) {
+    // ========================================================== weight producer (HBM stream)
+    // Weights depend on no earlier kernel: under programmatic dependent launch this warp streams ahead of
+    // griddepcontrol.wait.
+    const uint64_t pol = ptx::policy_evict_first();
+    RingPos wp{0, 0};
+    u32 it = 0;
+    SegIter si;
+    si.init(u0, u1, upt, n_tiles);
+    Seg sg;
+    while (si.next(sg, upt, n_tiles)) {
+      const uint8_t *wsrc = p.w.tiles + ((size_t)(p.w.col0 / kTileN + sg.tile)) * tile_stride + (size_t)sg.r0 * kStageBytes;
+#pragma unroll 1
+      for (int g = sg.r0; g < sg.r1; g++, it++, wsrc += kStageBytes, wp.advance(SW)) {
+        if (it >= (u32)SW) ptx::mbar_wait(bar(BAR_EMPTY_W + wp.st), wp.par ^ 1u);
+        if (ptx::elect_one()) {
+          const uint32_t full = bar(BAR_FULL_W + wp.st);
+          ptx::mbar_arrive_expect_tx(full, (uint32_t)kStageBytes);
+          ptx::bulk_g2s_hint(smem_base + kWBase + wp.st * kStageBytes, wsrc, kStageBytes, full, pol);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kWarpX) {
+    // ====================================================== activation producer (L2 hits)
+    if (lane == 0) ptx::prefetch_tensormap(xmap);
+    ptx::grid_dependency_wait();
+    RingPos xp{0, 0};
+    u32 it = 0;
+    SegIter si;
+    si.init(u0, u1, upt, n_tiles);
+    Seg sg;
+    while (si.next(sg, upt, n_tiles)) {
+      const int row0 = sg.blk * kNB;
+#pragma unroll 1
+      for (int g = sg.r0; g < sg.r1; g++, it++, xp.advance(SX)) {
+        const uint32_t slot_addr = smem_base + xp.st * kXBytes;
+        const uint32_t full = bar(BAR_FULL_X + xp.st);
+        if (it >= (u32)SX) ptx::mbar_wait(bar(BAR_EMPTY_X + xp.st), xp.par ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(full, (uint32_t)kXBytes);
+          // [16 rows x 64 k] boxes, hardware 128B swizzle; rows past the tensor end read as zero
+          ptx::tma_load_2d(slot_addr, xmap, g * kGroup, row0, full);
+          ptx::tma_load_2d(slot_addr + kNB * 128, xmap, g * kGroup + 64, row0, full);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // ==================================================================== MMA issuer
+    constexpr uint32_t idesc = ptx::umma_idesc_f16(128, kNB);
+    const uint64_t b_desc_ring = ptx::umma_desc_kmajor_sw128(smem_base);
+    RingPos xp{0, 0};
+#pragma unroll 1
+    for (u32 li = 0; li < n_units; li++, xp.advance(SX)) {
+      const uint32_t s = li & 1u;
+      ptx::mbar_wait(bar(BAR_FULL_X + xp.st), xp.par);            // activation slice landed (async-proxy write)
+      ptx::mbar_wait(bar(BAR_FULL_A + s), (li >> 1) & 1u);        // raw nibbles of the unit are in A slot s
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint64_t b0 = b_desc_ring + (uint64_t)((xp.st * kXBytes) >> 4);
+        const uint64_t b1 = b0 + (uint64_t)((kNB * 128) >> 4);    // second 64-k atom
+        const uint32_t a = tmem_base + kColA + s * 64;
+        const uint32_t d = tmem_base + kColD + s * kNB, d2 = tmem_base + kColD2 + s * kNB;
+        const uint32_t ones = tmem_base + kColOnes;
+        // hi class (q * 2^-20): k-steps 2, 3 of each 64-k half; the first MMA of a unit overwrites D
+        ptx::umma_f16_ts(d, a + 16, b0 + 4, idesc, 0u);
+        ptx::umma_f16_ts(d, a + 24, b0 + 6, idesc, 1u);
+        ptx::umma_f16_ts(d, a + 48, b1 + 4, idesc, 1u);
+        ptx::umma_f16_ts(d, a + 56, b1 + 6, idesc, 1u);
+        // lo class (q * 2^-24): D = A.B + D / 16 brings the hi sum to the same unit
+        ptx::umma_f16_ts_scaled<4>(d, a + 0, b0 + 0, idesc);
+        ptx::umma_f16_ts(d, a + 8, b0 + 2, idesc, 1u);
+        ptx::umma_f16_ts(d, a + 32, b1 + 0, idesc, 1u);
+        ptx::umma_f16_ts(d, a + 40, b1 + 2, idesc, 1u);
+        // D2 = ones . x^T: the sum of the group's activations, for the zero-point term
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) ptx::umma_f16_ts(d2, ones, b0 + (uint64_t)(kk * 2), idesc, kk != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) ptx::umma_f16_ts(d2, ones, b1 + (uint64_t)(kk * 2), idesc, 1u);
+        ptx::tc_commit(bar(BAR_DONE + s));                         // A slot s free, D[s] / D2[s] complete
+        ptx::tc_commit(bar(BAR_EMPTY_X + xp.st));                  // activation slot consumed
+      }
+      __syncwarp();
+    }
+  } else {
+    // ======================================================== dequant + accumulate + epilogue warps
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int s = warp >> 2;              // group: A slot / accumulator pair, parity of the units it takes
+    const int nl = q * 32 + lane;         // weight column inside the tile == TMEM lane
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t k_w = smem_base + kWBase + (uint32_t)nl * 16u, k_sz = smem_base + kWBase + kStageWBytes + (uint32_t)nl * 4u,
+             k_ta = lane_base + kColA + s * 64, k_d = lane_base + kColD + s * kNB, k_d2 = lane_base + kColD2 + s * kNB,
+             k_fa = bar(BAR_FULL_A + s), k_dn = bar(BAR_DONE + s), k_fw = bar(BAR_FULL_W), k_ew = bar(BAR_EMPTY_W);
+    // loop invariants through a self-shuffle: ptxas otherwise re-derives them from %tid in every iteration
+    k_w = __shfl_sync(0xffffffffu, k_w, lane); k_sz = __shfl_sync(0xffffffffu, k_sz, lane);
+    k_ta = __shfl_sync(0xffffffffu, k_ta, lane); k_d = __shfl_sync(0xffffffffu, k_d, lane);
+    k_d2 = __shfl_sync(0xffffffffu, k_d2, lane); k_fa = __shfl_sync(0xffffffffu, k_fa, lane);
+    k_dn = __shfl_sync(0xffffffffu, k_dn, lane); k_fw = __shfl_sync(0xffffffffu, k_fw, lane);
+    k_ew = __shfl_sync(0xffffffffu, k_ew, lane);
+    if (s == 0) {
+      // the constant ones operand (this group's first full_A arrival orders it before the first MMA)
+      uint32_t o8[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) o8[i] = 0x3C003C00u;
+      ptx::tmem_st_x8(lane_base + kColOnes, o8);
+    }
+    RingPos wp{s, 0};                     // this group's next unit is local unit s: ring stage s
+    uint32_t dpar = 0;                    // parity of BAR_DONE[s]
+    bool pending = false;                 // a unit of this group is in the tensor core: D[s] not accumulated yet
+    float sc_prev = 0.f, zs_prev = 0.f;   // its s * 2^24 and -s * z
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0.f;
+    bool dep_waited = false;
+    u32 lbase = 0;                        // local index of the segment's first unit
+    int seg = 0;
+    SegIter si;
+    si.init(u0, u1, upt, n_tiles);
+    Seg sg;
+
+    // Fold the finished unit of this group into the running sums (warp-collective).  Returning from the wait also
+    // means that A slot s is free again.
+    auto wait_done = [&]() {
+      ptx::mbar_wait(k_dn, dpar);
+      dpar ^= 1u;
+      ptx::tc_fence_after();
+    };
+    auto fold = [&]() {
+      uint32_t dv[R], ev[R];
+      tmem_ld_rows<R>(k_d, dv);
+      tmem_ld_rows<R>(k_d2, ev);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        acc[r] = fmaf(sc_prev, __uint_as_float(dv[r]), acc[r]);
+        acc[r] = fmaf(zs_prev, __uint_as_float(ev[r]), acc[r]);
+      }
+    };
+    // one 64-k half: two LDS.128 -> 16 lo-class + 16 hi-class half2 registers
+    auto convert_half = [&](const uint4 &wa, const uint4 &wb, uint32_t (&lo)[16], uint32_t (&hi)[16]) {
+      const uint32_t ws[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t w = ws[j], t = w >> 8;
+        lo[2 * j] = w & 0x000f000fu;
+        hi[2 * j] = w & 0x00f000f0u;
+        lo[2 * j + 1] = t & 0x000f000fu;
+        hi[2 * j + 1] = t & 0x00f000f0u;
+      }
+    };
+
+    while (si.next(sg, upt, n_tiles)) {
+      const int n_seg = sg.r1 - sg.r0;
+      // units of this segment that fall to this group: local indices lbase + j with parity s
+      int mine = 0;
+      {
+        const int j0 = (int)((lbase ^ (u32)s) & 1u);
+        if (n_seg > j0) mine = (n_seg - j0 + 1) >> 1;
+      }
+      lbase += (u32)n_seg;
+#pragma unroll 1
+      for (; mine > 0; mine--) {
+        const uint32_t stage_off = (uint32_t)wp.st * kStageBytes;
+        ptx::mbar_wait(k_fw + wp.st * 8, wp.par);
+        const uint32_t sz = ptx::lds32(k_sz + stage_off);
+        uint4 wa = ptx::lds128(k_w + stage_off);
+        uint4 wb = ptx::lds128(k_w + stage_off + 2048u);
+        uint32_t lo[16], hi[16];
+        convert_half(wa, wb, lo, hi);
+        wa = ptx::lds128(k_w + stage_off + 4096u);
+        wb = ptx::lds128(k_w + stage_off + 6144u);
+        if (pending) wait_done();                                 // MMAs of this group's previous unit are complete
+        ptx::tmem_st_x16(k_ta, lo);
+        ptx::tmem_st_x16(k_ta + 16, hi);
+        if (pending) fold();                                      // D[s] / D2[s] are read before the next MMAs overwrite them
+        convert_half(wa, wb, lo, hi);
+        // the packed words are in registers: release the weight stage to the HBM stream
+        if (lane == 0) ptx::mbar_arrive_after(k_ew + wp.st * 8, lo[15] ^ hi[15]);
+        ptx::tmem_st_x16(k_ta + 32, lo);
+        ptx::tmem_st_x16(k_ta + 48, hi);
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        if (lane == 0) ptx::mbar_arrive(k_fa);
+        __syncwarp();
+        const float sf = __half2float(__ushort_as_half((unsigned short)(sz & 0xFFFF)));
+        const float zf = __half2float(__ushort_as_half((unsigned short)(sz >> 16))) - 1024.0f;
+        sc_prev = sf * 16777216.0f;
+        zs_prev = -sf * zf;
+        pending = true;
+        wp.st += 2;
+        if (wp.st >= SW) { wp.st -= SW; wp.par ^= 1u; }
+      }
+
+      // ------------------------------------------------ epilogue of this tile segment
+      if (pending) {
+        wait_done();
+        fold();
+        ptx::tc_fence_before();
+        pending = false;
+      }
+      if (!dep_waited) {                  // before the first global write / scratch access
+        ptx::grid_dependency_wait();
+        dep_waited = true;
+      }
+      const int r_begin = sg.r0, r_end = sg.r1;
+      const int blk = sg.blk, tile = sg.tile, tau = sg.blk * n_tiles + sg.tile;
+      const int nv = min(kNB, p.rm.m - blk * kNB);               // real rows of the block (dense)
+      // the two groups swap the rows the other one finishes
+      float *xc = reinterpret_cast<float *>(smem + kXchgBase);
+      ptx::named_bar_sync(1, kDequantWarps * 32);                 // everybody is done reading the previous exchange
+      if constexpr (R <= 4) {
+        if (s == 1) {
+#pragma unroll
+          for (int r = 0; r < R; r++) xc[r * kTileN + nl] = acc[r];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < OWN; j++) xc[((1 - s) * OWN + j) * kTileN + nl] = acc[(1 - s) * OWN + j];
+      }
+      ptx::named_bar_sync(1, kDequantWarps * 32);
+      const bool has_rows = R > 4 || s == 0;
+      const int rb = R > 4 ? s * OWN : 0;                         // first row this group finishes
+      float v[OWN];
+#pragma unroll
+      for (int j = 0; j < OWN; j++) v[j] = (has_rows ? acc[rb + j] + xc[(rb + j) * kTileN + nl] : 0.f);
+#pragma unroll
+      for (int r = 0; r < R; r++) acc[r] = 0.f;
+      seg++;
+      if (!has_rows) continue;
+
+      constexpr int kPart = kNB * kTileN;
+      const int col = tile * kTileN + nl;
+      const float bias = p.w.bias ? p.w.bias[col] : 0.0f;
+      const bool whole = (r_begin == 0 && r_end == upt);         // this CTA covered the whole tile
+      const size_t push_off = push_world(p) ? ((size_t)(*(volatile const uint32_t *)p.push.epoch & 1u) * p.push.world +
+                                              p.push.rank) * p.push.slot_elems : 0;
+      int c_first = cta, c_last = cta;
+      if (!whole) {
+        const u32 tile_u0 = (u32)tau * (u32)upt;
+        c_first = cta_of_unit(tile_u0, T, G);
+        c_last = cta_of_unit(tile_u0 + upt - 1, T, G);
+      }
+      const bool owner = !whole && cta == c_first;
+      const bool ll = !whole && nv <= kLlRows && R <= kLlRows && G <= p.ll_ctas;
+      const int nr = nv - rb;                                    // real rows among this group's: j < nr
+      auto store_out = [&](int row_in_block, float val) {
+        const int cr = blk * kNB + row_in_block;
+        const __half hv = __float2half_rn(val + bias);
+        if (push_world(p) == 0) {
+          p.y[(size_t)cr * p.ld_out + col] = hv;
+        } else {
+          for (int r = 0; r < push_world(p); r++) p.push.data[r][push_off + (size_t)cr * p.ld_out + col] = hv;
+        }
+      };
+      if (whole) {
+#pragma unroll
+        for (int j = 0; j < OWN; j++)
+          if (j < nr) store_out(rb + j, v[j]);
+      } else if (ll) {
+        // ---- flag-in-value exchange (tc_gemm.cu): only the real rows travel, no counter, no fence
+        auto slot_of = [&](int c, int j) { return p.ll + (size_t)c * kLlFloatsPerCta + (size_t)((rb + j) * kTileN + nl); };
+        if (!owner) {
+#pragma unroll
+          for (int j = 0; j < OWN; j++)
+            if (j < nr) {
+              const uint32_t u = __float_as_uint(v[j]);
+              ptx::st_relaxed_u32(slot_of(cta, j), u == kLlEmpty ? 0x7fffffffu : u);
+            }
+        } else {
+          constexpr int UB = 8;                                  // contributors polled together
+#pragma unroll 1
+          for (int c0 = c_first + 1; c0 <= c_last; c0 += UB) {
+            uint32_t t[UB][OWN];
+#pragma unroll
+            for (int i = 0; i < UB; i++)
+#pragma unroll
+              for (int j = 0; j < OWN; j++)
+                t[i][j] = (j < nr && c0 + i <= c_last) ? ptx::ld_relaxed_u32(slot_of(c0 + i, j)) : 0u;
+#ifdef FB2_WAIT_TIMEOUT
+            const long long t0 = clock64();
+#endif
+            for (;;) {
+              bool waiting = false;
+#pragma unroll
+              for (int i = 0; i < UB; i++)
+#pragma unroll
+                for (int j = 0; j < OWN; j++) waiting |= t[i][j] == kLlEmpty;
+              if (!waiting) break;
+#pragma unroll
+              for (int i = 0; i < UB; i++)
+#pragma unroll
+                for (int j = 0; j < OWN; j++)
+                  if (t[i][j] == kLlEmpty) t[i][j] = ptx::ld_relaxed_u32(slot_of(c0 + i, j));
+#ifdef FB2_WAIT_TIMEOUT
+              if (clock64() - t0 > 4000000000LL) { printf("fb2: ll slot wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
+#endif
+            }
+#pragma unroll
+            for (int i = 0; i < UB; i++)
+#pragma unroll
+              for (int j = 0; j < OWN; j++)
+                if (j < nr && c0 + i <= c_last) {
+                  v[j] += __uint_as_float(t[i][j]);
+                  ptx::st_relaxed_u32(slot_of(c0 + i, j), kLlEmpty);   // consumed: empty again for the next launch
+                }
+          }
+#pragma unroll
+          for (int j = 0; j < OWN; j++)
+            if (j < nr) store_out(rb + j, v[j]);
+        }
+      } else {
+        // ---- counter exchange: partial tile + self-resetting arrival counter
+        if (owner) {
+          if (threadIdx.x == 0) {
+            const int need = c_last - c_first;
+#ifdef FB2_WAIT_TIMEOUT
+            const long long t0 = clock64();
+#endif
+            while (ptx::ld_acquire(p.counters + tau) < need) {
+#ifdef FB2_WAIT_TIMEOUT
+              if (clock64() - t0 > 4000000000LL) { printf("fb2: tile counter wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
+#endif
+            }
+            p.counters[tau] = 0;                                   // self-reset for the next launch
+          }
+          __syncwarp();
+          ptx::named_bar_sync(3, kEpiThreads);
+#pragma unroll 1
+          for (int c = c_first + 1; c <= c_last; c++) {
+            const float *src = p.partials + (size_t)c * kPart + (size_t)rb * kTileN + nl;
+            float t[OWN];
+#pragma unroll
+            for (int j = 0; j < OWN; j++) t[j] = j < nr ? __ldcg(src + (size_t)j * kTileN) : 0.f;
+#pragma unroll
+            for (int j = 0; j < OWN; j++) v[j] += t[j];
+          }
+#pragma unroll
+          for (int j = 0; j < OWN; j++)
+            if (j < nr) store_out(rb + j, v[j]);
+        } else {
+          float *part = p.partials + (size_t)cta * kPart + (size_t)rb * kTileN + nl;
+#pragma unroll
+          for (int j = 0; j < OWN; j++)
+            if (j < nr) part[(size_t)j * kTileN] = v[j];
+          ptx::named_bar_sync(3, kEpiThreads);                     // every partial store of the CTA is issued
+          if (threadIdx.x == 0) ptx::red_release_add(p.counters + tau, 1);
+          __syncwarp();
+        }
+      }
+    }
+    if (push_world(p)) {
+      // every participating CTA signals every rank once: its pushed tiles are complete
+      ptx::named_bar_sync(1, kDequantWarps * 32);
+      if (threadIdx.x == 0) {
+        const uint32_t par = *(volatile const uint32_t *)p.push.epoch & 1u;
+        __threadfence_system();
+        for (int r = 0; r < p.push.world; r++) atomicAdd_system(p.push.flags[r] + par * p.push.world + p.push.rank, 1u);
+      }
+      __syncwarp();
+    }
+  }
+
+  // -------------------------------------------------------------------------- teardown
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+template <int R, bool kPush>
+__global__ void __launch_bounds__(384, 2) dk_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
+  ptx::launch_dependents();
+  dk_body<R, kPush>(p, &xmap);
+}
+
+}  // namespace dk

@@ -140,58 +140,18 @@ constexpr uint32_t kLlEmpty = 0xffffffffu;
 constexpr int kLlFloatsPerCta = 2 * kLlRows * kTileN;
 static_assert((size_t)kLlMaxCtas * kLlFloatsPerCta * sizeof(uint32_t) == kLlBytes, "ll area size");
 
-// Dequantise one packed word (nibble p holds k offset {0,2,4,6,1,3,5,7}[p]) into 4 half2
-// registers (k0,k1) (k2,k3) (k4,k5) (k6,k7).
+// Dequantise one packed word (tile_nibble_k: even nibbles = "lo class", odd = "hi class") into 4 half2
+// registers: lo[0] = nibbles (0,4), lo[1] = nibbles (2,6) -- consecutive A columns of the lo k-steps --
+// and hi[0] = nibbles (1,5), hi[1] = nibbles (3,7) of the hi k-steps.
 __device__ __forceinline__ void dequant_word(uint32_t q, __half2 zlo, __half2 zhi, __half2 s2,
-                                             uint32_t *out) {
-#ifdef FB2_EXP_RAW_NIBBLES
-  // Timing probe for the round-2 plan ("Next (a)"): the nibbles go to the tensor core as fp16
-  // SUBNORMALS (q * 2^-24 from bits 3:0, q * 2^-20 from bits 7:4 of each half) -- 5 instructions a word instead of
-  // 13 -- and scale / zero point would move to the accumulator side.  That side is not written yet, so a build
-  // with this macro is NUMERICALLY WRONG on purpose; it is never defined in the product build and exists to time
-  // the dequant loop (scripts/build_variant.sh rawnib "-DFB2_EXP_RAW_NIBBLES", FB2_LIB=..., scripts/shape_sweep.py).
-  (void)zlo; (void)zhi; (void)s2;
-  const uint32_t q2r = q >> 8;
-  out[0] = q & 0x000f000fu;
-  out[1] = q & 0x00f000f0u;
-  out[2] = q2r & 0x000f000fu;
-  out[3] = q2r & 0x00f000f0u;
-  return;
-#endif
-#ifdef FB2_EXP_NO_ZERO
-  // Second timing probe: f16_rn(q * s) with ONE fma per half2 -- fma(1024 + q, s, -1024 s) and
-  // fma(1024 + 16 q, s / 16, -64 s), both constants exact -- 9 instructions a word; the zero term -z s Sum(x) would go
-  // through one extra MMA k-step per unit.  That k-step is not written yet: NUMERICALLY WRONG on purpose, never in the
-  // product build.
-  (void)zlo; (void)zhi;
-  {
-    const uint32_t kMagicP = 0x64006400u;
-    const __half2 s16 = __hmul2(s2, __float2half2_rn(0.0625f));
-    const __half2 c_lo = __hmul2(s2, __float2half2_rn(-1024.0f));
-    const __half2 c_hi = __hmul2(s2, __float2half2_rn(-64.0f));
-    uint32_t a0 = ptx::lop3_and_or(q, 0x000f000fu, kMagicP);
-    uint32_t b0 = ptx::lop3_and_or(q, 0x00f000f0u, kMagicP);
-    const uint32_t qq = q >> 8;
-    uint32_t a1 = ptx::lop3_and_or(qq, 0x000f000fu, kMagicP);
-    uint32_t b1 = ptx::lop3_and_or(qq, 0x00f000f0u, kMagicP);
-    __half2 w0 = __hfma2(*reinterpret_cast<__half2 *>(&a0), s2, c_lo);
-    __half2 w1 = __hfma2(*reinterpret_cast<__half2 *>(&b0), s16, c_hi);
-    __half2 w2 = __hfma2(*reinterpret_cast<__half2 *>(&a1), s2, c_lo);
-    __half2 w3 = __hfma2(*reinterpret_cast<__half2 *>(&b1), s16, c_hi);
-    out[0] = *reinterpret_cast<uint32_t *>(&w0);
-    out[1] = *reinterpret_cast<uint32_t *>(&w1);
-    out[2] = *reinterpret_cast<uint32_t *>(&w2);
-    out[3] = *reinterpret_cast<uint32_t *>(&w3);
-    return;
-  }
-#endif
+                                             uint32_t *lo, uint32_t *hi) {
   const uint32_t kMagic = 0x64006400u;                 // half2(1024, 1024)
   const __half2 k16th = __float2half2_rn(0.0625f);
-  uint32_t lo0 = ptx::lop3_and_or(q, 0x000f000fu, kMagic);   // 1024 + q      (k0,k1)
-  uint32_t hi0 = ptx::lop3_and_or(q, 0x00f000f0u, kMagic);   // 1024 + 16 q   (k2,k3)
+  uint32_t lo0 = ptx::lop3_and_or(q, 0x000f000fu, kMagic);   // 1024 + q
+  uint32_t hi0 = ptx::lop3_and_or(q, 0x00f000f0u, kMagic);   // 1024 + 16 q
   uint32_t q2 = q >> 8;
-  uint32_t lo1 = ptx::lop3_and_or(q2, 0x000f000fu, kMagic);  //               (k4,k5)
-  uint32_t hi1 = ptx::lop3_and_or(q2, 0x00f000f0u, kMagic);  //               (k6,k7)
+  uint32_t lo1 = ptx::lop3_and_or(q2, 0x000f000fu, kMagic);
+  uint32_t hi1 = ptx::lop3_and_or(q2, 0x00f000f0u, kMagic);
   __half2 v0 = __hsub2(*reinterpret_cast<__half2 *>(&lo0), zlo);          // q - z, exact
   __half2 v1 = __hfma2(*reinterpret_cast<__half2 *>(&hi0), k16th, zhi);   // q - z, exact
   __half2 v2 = __hsub2(*reinterpret_cast<__half2 *>(&lo1), zlo);
@@ -200,10 +160,10 @@ __device__ __forceinline__ void dequant_word(uint32_t q, __half2 zlo, __half2 zh
   v1 = __hmul2(v1, s2);
   v2 = __hmul2(v2, s2);
   v3 = __hmul2(v3, s2);
-  out[0] = *reinterpret_cast<uint32_t *>(&v0);
-  out[1] = *reinterpret_cast<uint32_t *>(&v1);
-  out[2] = *reinterpret_cast<uint32_t *>(&v2);
-  out[3] = *reinterpret_cast<uint32_t *>(&v3);
+  lo[0] = *reinterpret_cast<uint32_t *>(&v0);
+  hi[0] = *reinterpret_cast<uint32_t *>(&v1);
+  lo[1] = *reinterpret_cast<uint32_t *>(&v2);
+  hi[1] = *reinterpret_cast<uint32_t *>(&v3);
 }
 
 // CH (8 or 16) consecutive fp32 accumulator columns of this thread's lane
@@ -597,15 +557,15 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         const __half2 zlo = __half2half2(zl);
         const __half2 zhi = __hsub2(__float2half2_rn(960.0f), zlo);       // -(64 + z), exact
 
-        uint32_t r0[16], r1[16];
-        dequant_word(w0.x, zlo, zhi, s2, r0 + 0);
-        dequant_word(w0.y, zlo, zhi, s2, r0 + 4);
-        dequant_word(w0.z, zlo, zhi, s2, r0 + 8);
-        dequant_word(w0.w, zlo, zhi, s2, r0 + 12);
-        dequant_word(w1.x, zlo, zhi, s2, r1 + 0);
-        dequant_word(w1.y, zlo, zhi, s2, r1 + 4);
-        dequant_word(w1.z, zlo, zhi, s2, r1 + 8);
-        dequant_word(w1.w, zlo, zhi, s2, r1 + 12);
+        uint32_t r0[16], r1[16];                                  // A columns [0,16) = lo class, [16,32) = hi class
+        dequant_word(w0.x, zlo, zhi, s2, r0 + 0, r1 + 0);
+        dequant_word(w0.y, zlo, zhi, s2, r0 + 2, r1 + 2);
+        dequant_word(w0.z, zlo, zhi, s2, r0 + 4, r1 + 4);
+        dequant_word(w0.w, zlo, zhi, s2, r0 + 6, r1 + 6);
+        dequant_word(w1.x, zlo, zhi, s2, r0 + 8, r1 + 8);
+        dequant_word(w1.y, zlo, zhi, s2, r0 + 10, r1 + 10);
+        dequant_word(w1.z, zlo, zhi, s2, r0 + 12, r1 + 12);
+        dequant_word(w1.w, zlo, zhi, s2, r0 + 14, r1 + 14);
         // the packed words are in registers (consumed, not merely requested): release the weight
         // stage to the HBM stream now -- it does not wait for the MMA.  The arrive is predicated (no
         // divergence, so no reconvergence point is needed) and tied to the last dequantised words.
@@ -954,6 +914,8 @@ __global__ void __launch_bounds__(256) p2p_reduce_kernel(const __half *__restric
   }
 }
 
+#include "tc_decode.cuh"
+
 // ------------------------------------------------------------------------ host planning
 struct TcPlan {
   int nb, row_blocks, n_tiles, nacc, grid, whole_tiles;
@@ -1064,6 +1026,27 @@ int launch_plain(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const
   FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NB, kSilu, kPush>, p, xmap));
   return FB2_OK;
 }
+// decode-batch kernel (tc_decode.cuh): dense rows, <= 16 of them, activations through the tensor map
+template <int R, bool kPush>
+int launch_dk(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
+  static const cudaError_t attr_rc =
+      cudaFuncSetAttribute(dk::dk_gemm_kernel<R, kPush>, cudaFuncAttributeMaxDynamicSharedMemorySize, dk::kSmemBytes);
+  FB2_CUDA_TRY(attr_rc);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  launch_cfg(cfg, attr, pl, stream);
+  cfg.dynamicSmemBytes = dk::kSmemBytes;
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, dk::dk_gemm_kernel<R, kPush>, p, xmap));
+  return FB2_OK;
+}
+template <bool kPush>
+int launch_dk_rows(int m, const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
+  return m <= 1 ? launch_dk<1, kPush>(pl, stream, p, xmap)
+         : m <= 2 ? launch_dk<2, kPush>(pl, stream, p, xmap)
+         : m <= 4 ? launch_dk<4, kPush>(pl, stream, p, xmap)
+         : m <= 8 ? launch_dk<8, kPush>(pl, stream, p, xmap) : launch_dk<16, kPush>(pl, stream, p, xmap);
+}
+
 template <int NB>
 int launch_dispatch(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap,
                     const DispatchTable &tbl) {
@@ -1223,7 +1206,12 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   }
 #endif
   int rc;
-  if (push && push->world) {
+  static const bool no_dk = [] { const char *e = getenv("FB2_DEBUG_NO_DK"); return e && e[0] == '1'; }();
+  const bool use_dk = !no_dk && rows.mode == ROWS_DENSE && nb == 16 && !epilogue && !tbl && (p.x_tma & 1);
+  if (use_dk) {
+    rc = (push && push->world) ? launch_dk_rows<true>(rows.m, pl, stream, p, xmap)
+                               : launch_dk_rows<false>(rows.m, pl, stream, p, xmap);
+  } else if (push && push->world) {
     if (tbl || epilogue || nb > 64) {
       set_error("fused all-reduce: decode-sized dense launches only (<= 64 rows per block)");
       return FB2_ERR_UNSUPPORTED;
