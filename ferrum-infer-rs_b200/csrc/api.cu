@@ -411,7 +411,9 @@ static int run_tc(const WeightRef &w_in, const RowMap &rm, const DispatchTable *
     if ((rc = grow_xperm(device, xb))) return rc;
     sc = current_scratch(device, &sms);
   }
-  if (w.perm) {
+  if (w.perm && dk_gather_ok(w, rm, tbl, epilogue) && ((uintptr_t)x % 16) == 0) {
+    // act-order, decode batch: the kernel copies the rows of x into shared memory and gathers there
+  } else if (w.perm) {
     // act-order: A'[m, j] = A[m, perm[j]] once per GEMM (reference: gather_columns.cu:15 via
     // marlin_gemm_with_perm, quant.rs:434-509); every CTA then loads its slice with 16-byte
     // vectors instead of repeating the gather per weight tile.

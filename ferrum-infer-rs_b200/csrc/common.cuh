@@ -181,6 +181,8 @@ struct TcScratch {
 constexpr int kLlMaxCtas = 1024;                 // >= 2 CTAs per SM on any sm_100 part
 constexpr size_t kLlBytes = (size_t)kLlMaxCtas * 2 * 8 * 128 * sizeof(uint32_t);   // [ctas][2 acc][8 rows][128]
 bool tc_supported(const WeightRef &w);
+// act-order launches the decode kernel gathers itself (no permute launch, w.perm stays set)
+bool dk_gather_ok(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue);
 // Split-K scratch one launch with these rows needs (0 / 0 when it does not split).
 void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count,
                      size_t *partial_bytes, size_t *counters);

@@ -120,6 +120,10 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void *src
       ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
+// Bulk prefetch global -> L2 (no destination, no completion signal).
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // 16-byte cp.async (LDGSTS) global -> shared, and its mbarrier completion hook.
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
@@ -303,6 +307,21 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const void *addr) {
 }
 __device__ __forceinline__ void st_relaxed_u32(void *addr, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+// vector forms: every 32-bit element is its own flag-in-value slot (element-wise atomicity is all that is needed)
+__device__ __forceinline__ void ld_relaxed_v2(const void *addr, uint32_t (&v)[2]) {
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "l"(addr) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_v4(const void *addr, uint32_t (&v)[4]) {
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(addr) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_v2(void *addr, const uint32_t (&v)[2]) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(addr), "r"(v[0]), "r"(v[1]) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_v4(void *addr, const uint32_t (&v)[4]) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *addr) {
   uint32_t v;

@@ -19,6 +19,27 @@ namespace sched {
 // critical path twice: before the first weight request of every CTA and in front of every fix-up.
 typedef unsigned int u32;
 FB2_HD u32 range_start(u32 c, u32 T, u32 G) { return c * T / G; }
+// Division by a launch constant without the ~40-instruction emulated divide: the host passes floor(2^32 / d); the
+// estimate hi32(n * magic) is the quotient or one below it for every 32-bit n.  (The divides sat on the path from CTA
+// entry to the first weight request of the decode kernel: four of them were ~0.4 us of a single warp's time.)
+struct FastDiv {
+  u32 d, magic;
+};
+FB2_HD FastDiv make_fastdiv(u32 d) {
+  FastDiv f;
+  f.d = d;
+  f.magic = d > 1 ? (u32)(0x100000000ULL / d) : 0xFFFFFFFFu;
+  return f;
+}
+FB2_HD u32 fdiv(u32 n, FastDiv f) {
+#if defined(__CUDA_ARCH__)
+  u32 q = __umulhi(n, f.magic);
+#else
+  u32 q = (u32)(((unsigned long long)n * f.magic) >> 32);
+#endif
+  if (n - q * f.d >= f.d) q++;
+  return q;
+}
 // Tiles of only a few units (K <= 1024: the MoE down projection has 6) are never split: cutting one
 // costs a partial-tile fix-up (~3 us) that is longer than streaming the whole tile.  CTA c then owns
 // the whole tiles [c * NT / G, (c + 1) * NT / G) -- when that balances: at most one tile per CTA, or so
@@ -35,6 +56,13 @@ FB2_HD int cta_of_unit(u32 u, u32 T, u32 G) {
   return (int)c;
 }
 
+FB2_HD int cta_of_unit_fd(u32 u, FastDiv T, FastDiv G) {
+  u32 c = fdiv(u * G.d, T);
+  while (c + 1 < G.d && fdiv((c + 1) * T.d, G) <= u) c++;
+  while (c > 0 && fdiv(c * T.d, G) > u) c--;
+  return (int)c;
+}
+
 // One CTA's unit range, cut into SEGMENTS: maximal runs of units that belong to one output
 // tile (row block, tile).  r0/r1 index the tile's unit list [gate groups..., up groups...].
 struct Seg {
@@ -48,6 +76,14 @@ struct SegIter {
     r = (int)(u0 - tau * (u32)upt);
     blk = (int)(tau / (u32)n_tiles);
     tile = (int)(tau - (u32)blk * (u32)n_tiles);
+    left = (int)(u1 - u0);
+    first = 1;
+  }
+  FB2_HD void init_fd(u32 u0, u32 u1, FastDiv upt, FastDiv n_tiles) {
+    const u32 tau = fdiv(u0, upt);
+    r = (int)(u0 - tau * upt.d);
+    blk = (int)fdiv(tau, n_tiles);
+    tile = (int)(tau - (u32)blk * n_tiles.d);
     left = (int)(u1 - u0);
     first = 1;
   }

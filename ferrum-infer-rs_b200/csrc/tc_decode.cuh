@@ -8,10 +8,12 @@
 //     round 2).  The tile format keeps every MMA k-step class-pure (common.cuh, tile_nibble_k); the four hi-class
 //     k-steps of a unit are issued first and the first lo-class MMA carries scale-input-d = 4
 //     (D = A.B + D * 2^-4), so one accumulator holds 2^-24 * sum_k q_k x_k exactly.
-//   * SCALE AND ZERO POINT ON THE ACCUMULATOR SIDE.  Every unit (one 128 x 128 stage) gets a FRESH accumulator
-//     D[slot] and a second one, D2[slot] = ones . x^T = sum_k x_k of the group (eight more MMAs against a constant
-//     all-ones A operand of 8 TMEM columns).  The dequant warps read both back (tcgen05.ld, R columns = real rows)
-//     and keep the running sum in REGISTERS: acc[r] += (s 2^24) D[r] - (s z) D2[r], two fp32 FMAs per row and unit
+//   * ZERO POINT ON THE TENSOR CORE, SCALE ON THE ACCUMULATOR SIDE.  Every unit (one 128 x 128 stage) gets a FRESH
+//     accumulator D[slot].  The zero point is constant per (group, column) = per unit and TMEM lane, and the term
+//     it contributes, -z * sum_k x_k, is linear: eight more MMAs run the unit's activation slice against an A
+//     operand of 8 TMEM columns that hold half2(-z, -z) * 2^-24 (one tcgen05.st per unit), accumulating into the
+//     same D.  D = 2^-24 * sum_k (q_k - z) x_k; the dequant warps read it back (tcgen05.ld, R columns = real
+//     rows) and keep the running sum in REGISTERS: acc[r] += (s * 2^24) * D[r] -- one fp32 FMA per row and unit
 //     instead of three fp16 instructions per weight pair.  The weight is never rounded to fp16: results are closer
 //     to the f64 reference than the prefill path's.
 //   * TWO UNITS IN FLIGHT PER CTA.  The eight dequant warps form two groups of four (one warp per TMEM lane
@@ -30,21 +32,24 @@ constexpr int kNB = 16;                     // UMMA N: rows of a block (<= 16 re
 constexpr int kXSlots = 4;
 constexpr int kXBytes = kNB * 256;          // [2 atoms][16 rows][128 B]
 constexpr int kXchgBytes = 16 * kTileN * 4; // group <-> group exchange of partial sums
-constexpr int kSmemBudget = 108 * 1024;
-constexpr int kWBase = kXSlots * kXBytes;   // 1024-aligned
-constexpr int kWStages = (kSmemBudget - 1024 - kWBase - kXchgBytes) / kStageBytes;      // 9
-constexpr int kXchgBase = kWBase + kWStages * kStageBytes;
-constexpr int kBarBase = (kXchgBase + kXchgBytes + 127) & ~127;
-constexpr int kSmemBytes = kBarBase + 1024;
-static_assert(kWStages >= 4 && kWStages <= kMaxWStages, "weight ring depth");
-// tensor memory columns (256 allocated): A slots, per-slot accumulators, the constant ones operand
+constexpr int kSmemBudget = 108 * 1024;     // two CTAs per SM
+// shared memory: [X slots][exchange][barriers + misc][weight ring: run-time depth][act-order: the x rows, natural order]
+constexpr int kXchgBase = kXSlots * kXBytes;
+constexpr int kBarBase = kXchgBase + kXchgBytes;
+constexpr int kWBase = kBarBase + 1024;
+constexpr int kMinWStages = 5;
+__host__ __device__ constexpr int w_stages_for(int xs_bytes) {
+  return (kSmemBudget - kWBase - xs_bytes) / kStageBytes < kMaxWStages ? (kSmemBudget - kWBase - xs_bytes) / kStageBytes
+                                                                      : kMaxWStages;
+}
+static_assert(w_stages_for(0) >= 8, "weight ring depth");
+// tensor memory columns (256 allocated): A slots, per-slot accumulators, per-slot zero-point operand
 constexpr int kTmemCols = 256;
 constexpr int kColA = 0;                    // 2 slots x 64
-constexpr int kColD = 128;                  // 2 x 16: sum_k q_k x_k * 2^-24
-constexpr int kColD2 = 160;                 // 2 x 16: sum_k x_k
-constexpr int kColOnes = 192;               // 8 columns of half2(1, 1)
+constexpr int kColD = 128;                  // 2 x 16: 2^-24 * sum_k (q_k - z) x_k
+constexpr int kColZ = 160;                  // 2 x 8 columns of half2(-z, -z) * 2^-24
 enum { BAR_FULL_W = 0, BAR_EMPTY_W = kMaxWStages, BAR_FULL_X = 2 * kMaxWStages, BAR_EMPTY_X = BAR_FULL_X + kXSlots,
-       BAR_FULL_A = BAR_EMPTY_X + kXSlots, BAR_DONE = BAR_FULL_A + 2, BAR_COUNT = BAR_DONE + 2 };
+       BAR_FULL_A = BAR_EMPTY_X + kXSlots, BAR_DONE = BAR_FULL_A + 2, BAR_XS = BAR_DONE + 2, BAR_COUNT = BAR_XS + 1 };
 static_assert(BAR_COUNT * 8 <= 512, "barrier area too small");
 
 template <int R>
@@ -56,28 +61,53 @@ __device__ __forceinline__ void tmem_ld_rows(uint32_t taddr, uint32_t (&r)[R]) {
   else ptx::tmem_ld_x16(taddr, r);
 }
 
+template <int VW>
+__device__ __forceinline__ void ld_slots(const uint32_t *a, uint32_t (&o)[VW]) {
+  if constexpr (VW == 1) o[0] = ptx::ld_relaxed_u32(a);
+  else if constexpr (VW == 2) ptx::ld_relaxed_v2(a, o);
+  else ptx::ld_relaxed_v4(a, o);
+}
+template <int VW>
+__device__ __forceinline__ void st_slots(uint32_t *a, const uint32_t (&u)[VW]) {
+  if constexpr (VW == 1) ptx::st_relaxed_u32(a, u[0]);
+  else if constexpr (VW == 2) ptx::st_relaxed_v2(a, u);
+  else ptx::st_relaxed_v4(a, u);
+}
+template <int VW>
+__device__ __forceinline__ void reset_slots(uint32_t *a) {     // plain stores: the kernel boundary publishes them
+  if constexpr (VW == 1) *a = 0xffffffffu;
+  else if constexpr (VW == 2) *reinterpret_cast<uint2 *>(a) = make_uint2(0xffffffffu, 0xffffffffu);
+  else *reinterpret_cast<uint4 *>(a) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+}
+
 // R = accumulator columns each dequant thread reads per unit: the real rows of a block rounded up to a power of two.
-template <int R, bool kPush>
+// kGather: act-order layer whose activation rows fit in shared memory next to the weight ring -- the CTA copies
+// the m rows of x (natural column order) once and the activation producer gathers x[r, perm[k']] per unit from that
+// copy straight into the swizzled UMMA B layout: no permute launch in front of the GEMM, no second dependency hop.
+template <int R, bool kPush, bool kGather>
 __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "rows per thread");
-  constexpr int SW = kWStages, SX = kXSlots;
+  constexpr int SX = kXSlots;
+  const int SW = p.w_stages;                                     // weight ring depth (host: w_stages_for)
   constexpr int OWN = R <= 4 ? R : R / 2;           // rows a group finishes in the epilogue (group 1: none when R <= 4)
   constexpr int kEpiThreads = R <= 4 ? 128 : 256;   // threads that take part in the inter-CTA exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FB2_TL(0);
+  if (warp == kWarpW) FB2_TLW(16);
   const int G = (int)gridDim.x;
   const int cta = (int)blockIdx.x;
   const int groups = p.groups, n_tiles = p.n_tiles;
   const int upt = groups;                                        // units per output tile
-  const u32 T = (u32)rowmap_num_blocks(p.rm, kNB) * (u32)n_tiles * (u32)upt;
+  const u32 T = p.fd_units.d;                                    // dense rows, one block: n_tiles * upt
   u32 u0, u1;
   if (p.whole_tiles) {
-    u0 = tile_range_start(cta, T / upt, G, upt);
-    u1 = tile_range_start(cta + 1, T / upt, G, upt);
+    u0 = fdiv((u32)cta * (u32)n_tiles, p.fd_grid) * (u32)upt;
+    u1 = fdiv((u32)(cta + 1) * (u32)n_tiles, p.fd_grid) * (u32)upt;
   } else {
-    u0 = range_start(cta, T, G);
-    u1 = range_start(cta + 1, T, G);
+    u0 = fdiv((u32)cta * T, p.fd_grid);
+    u1 = fdiv((u32)(cta + 1) * T, p.fd_grid);
   }
   if (u0 >= u1) return;                                          // CTA-uniform, before any barrier
 
@@ -89,21 +119,21 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
 
   // ------------------------------------------------------------------ one-time setup
   if (warp == kWarpW) {
-    if (lane == 0) {
-      for (int i = 0; i < SW; i++) {
-        ptx::mbar_init(bar(BAR_FULL_W + i), 1);                  // the producer's arrive.expect_tx
-        ptx::mbar_init(bar(BAR_EMPTY_W + i), 4);                 // read into registers by the 4 warps of one group
-      }
-      ptx::mbar_fence_init();
+    // one barrier pair per lane; the CTA-wide arrive follows the first weight request (below)
+    if (lane < SW) {
+      ptx::mbar_init(bar(BAR_FULL_W + lane), 1);                 // the producer's arrive.expect_tx
+      ptx::mbar_init(bar(BAR_EMPTY_W + lane), 4);                // read into registers by the 4 warps of one group
     }
+    ptx::mbar_fence_init();
     __syncwarp();
-    ptx::named_bar_arrive(2, kThreads);
+    FB2_TLW(17);
   } else if (warp == kWarpX) {
     if (lane == 0) {
       for (int i = 0; i < SX; i++) {
         ptx::mbar_init(bar(BAR_FULL_X + i), 1);
         ptx::mbar_init(bar(BAR_EMPTY_X + i), 1);                 // the MMA commit
       }
+      ptx::mbar_init(bar(BAR_XS), 1);
       ptx::mbar_fence_init();
     }
     __syncwarp();
@@ -127,6 +157,11 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
     tmem_base = *s_tmem;
   }
   const u32 n_units = u1 - u0;
+  FB2_TL(1);
+  FB2_TLV(8, n_units);
+#ifdef FB2_TRACE
+  { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); FB2_TLV(10, smid); }
+#endif
 
   if (warp == kWarpW) {
     // ========================================================== weight producer (HBM stream)
@@ -136,30 +171,61 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
     RingPos wp{0, 0};
     u32 it = 0;
     SegIter si;
-    si.init(u0, u1, upt, n_tiles);
+    si.init_fd(u0, u1, p.fd_upt, p.fd_tiles);
     Seg sg;
+    FB2_TLW(18);
     while (si.next(sg, upt, n_tiles)) {
       const uint8_t *wsrc = p.w.tiles + ((size_t)(p.w.col0 / kTileN + sg.tile)) * tile_stride + (size_t)sg.r0 * kStageBytes;
+      if (p.l2_prefetch && ptx::elect_one()) {
+        // ask for the whole segment now: the HBM stream no longer depends on the ring's turnaround
+        const uint32_t bytes = (uint32_t)(sg.r1 - sg.r0) * kStageBytes;
+        for (uint32_t off = 0; off < bytes; off += 8 * kStageBytes)
+          ptx::bulk_prefetch_l2(wsrc + off, bytes - off < 8u * kStageBytes ? bytes - off : 8u * kStageBytes);
+      }
+      __syncwarp();
 #pragma unroll 1
       for (int g = sg.r0; g < sg.r1; g++, it++, wsrc += kStageBytes, wp.advance(SW)) {
         if (it >= (u32)SW) ptx::mbar_wait(bar(BAR_EMPTY_W + wp.st), wp.par ^ 1u);
+        if (it == 0) FB2_TLW(11);
         if (ptx::elect_one()) {
           const uint32_t full = bar(BAR_FULL_W + wp.st);
           ptx::mbar_arrive_expect_tx(full, (uint32_t)kStageBytes);
           ptx::bulk_g2s_hint(smem_base + kWBase + wp.st * kStageBytes, wsrc, kStageBytes, full, pol);
         }
         __syncwarp();
+        if (it == 0) ptx::named_bar_arrive(2, kThreads);         // ring barriers are initialised (setup barrier)
       }
     }
   } else if (warp == kWarpX) {
     // ====================================================== activation producer (L2 hits)
-    if (lane == 0) ptx::prefetch_tensormap(xmap);
+    if (!kGather && lane == 0) ptx::prefetch_tensormap(xmap);
+    const int m = p.rm.m;
+    const uint32_t xs_base = smem_base + kWBase + (uint32_t)SW * kStageBytes;   // kGather: x rows [m][K], natural order
+    int4 pm = make_int4(0, 0, 0, 0);                              // kGather: perm of the next unit, 4 k' per lane
+    SegIter si;
+    si.init_fd(u0, u1, p.fd_upt, p.fd_tiles);
+    Seg sg;
+    if (kGather) {
+      // rows >= m of the slots are never written by the gather: clear them once (they feed accumulator columns
+      // nobody reads, but they should not hold NaN patterns either); perm is a weight-side constant
+      for (int i = lane; i < SX * kXBytes / 16; i += 32)
+        *reinterpret_cast<uint4 *>(smem + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+      const int g_first = (int)(u0 % (u32)upt);
+      pm = __ldg(reinterpret_cast<const int4 *>(p.w.perm + (size_t)g_first * kGroup) + lane);
+    }
     ptx::grid_dependency_wait();
+    FB2_TLW(12);
+    if (kGather) {
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(bar(BAR_XS), (uint32_t)m * (uint32_t)p.w.k * 2u);
+        for (int r = 0; r < m; r++)
+          ptx::bulk_g2s(xs_base + (uint32_t)r * (uint32_t)p.w.k * 2u, p.x + (size_t)r * p.w.k, (uint32_t)p.w.k * 2u, bar(BAR_XS));
+      }
+      __syncwarp();
+      ptx::mbar_wait(bar(BAR_XS), 0);
+    }
     RingPos xp{0, 0};
     u32 it = 0;
-    SegIter si;
-    si.init(u0, u1, upt, n_tiles);
-    Seg sg;
     while (si.next(sg, upt, n_tiles)) {
       const int row0 = sg.blk * kNB;
 #pragma unroll 1
@@ -167,13 +233,38 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
         const uint32_t slot_addr = smem_base + xp.st * kXBytes;
         const uint32_t full = bar(BAR_FULL_X + xp.st);
         if (it >= (u32)SX) ptx::mbar_wait(bar(BAR_EMPTY_X + xp.st), xp.par ^ 1u);
-        if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(full, (uint32_t)kXBytes);
-          // [16 rows x 64 k] boxes, hardware 128B swizzle; rows past the tensor end read as zero
-          ptx::tma_load_2d(slot_addr, xmap, g * kGroup, row0, full);
-          ptx::tma_load_2d(slot_addr + kNB * 128, xmap, g * kGroup + 64, row0, full);
+        if (!kGather) {
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(full, (uint32_t)kXBytes);
+            // [16 rows x 64 k] boxes, hardware 128B swizzle; rows past the tensor end read as zero
+            ptx::tma_load_2d(slot_addr, xmap, g * kGroup, row0, full);
+            ptx::tma_load_2d(slot_addr + kNB * 128, xmap, g * kGroup + 64, row0, full);
+          }
+          __syncwarp();
+        } else {
+          // lane l builds k' = 4l .. 4l+3 of every real row: 8 bytes inside one 16-byte chunk of the swizzled row
+          const int4 cur = pm;
+          {
+            // perm of the unit after this one (the next group of the tile, or group 0 of the next tile)
+            const int gn = g + 1 < upt ? g + 1 : 0;
+            pm = __ldg(reinterpret_cast<const int4 *>(p.w.perm + (size_t)gn * kGroup) + lane);
+          }
+          const uint32_t chunk = (uint32_t)(lane >> 1) & 7u, atom = (uint32_t)lane >> 4, sub = (uint32_t)(lane & 1) * 8u;
+#pragma unroll 2
+          for (int r = 0; r < m; r++) {
+            const uint32_t row = xs_base + (uint32_t)r * (uint32_t)p.w.k * 2u;
+            uint32_t v0, v1, v2, v3;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v0) : "r"(row + (uint32_t)cur.x * 2u));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v1) : "r"(row + (uint32_t)cur.y * 2u));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v2) : "r"(row + (uint32_t)cur.z * 2u));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v3) : "r"(row + (uint32_t)cur.w * 2u));
+            const uint32_t dst = slot_addr + atom * (kNB * 128) + (uint32_t)r * 128u + ((chunk ^ ((uint32_t)r & 7u)) << 4) + sub;
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(dst), "r"(v0 | (v1 << 16)), "r"(v2 | (v3 << 16)) : "memory");
+          }
+          ptx::fence_proxy_async_smem();                         // generic-proxy writes -> visible to the UMMA reads
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(full);
         }
-        __syncwarp();
       }
     }
   } else if (warp == kWarpMma) {
@@ -185,14 +276,15 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
     for (u32 li = 0; li < n_units; li++, xp.advance(SX)) {
       const uint32_t s = li & 1u;
       ptx::mbar_wait(bar(BAR_FULL_X + xp.st), xp.par);            // activation slice landed (async-proxy write)
+      if (li == 0) FB2_TLW(13);
       ptx::mbar_wait(bar(BAR_FULL_A + s), (li >> 1) & 1u);        // raw nibbles of the unit are in A slot s
+      if (li == 0) FB2_TLW(14);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint64_t b0 = b_desc_ring + (uint64_t)((xp.st * kXBytes) >> 4);
         const uint64_t b1 = b0 + (uint64_t)((kNB * 128) >> 4);    // second 64-k atom
         const uint32_t a = tmem_base + kColA + s * 64;
-        const uint32_t d = tmem_base + kColD + s * kNB, d2 = tmem_base + kColD2 + s * kNB;
-        const uint32_t ones = tmem_base + kColOnes;
+        const uint32_t d = tmem_base + kColD + s * kNB, zc = tmem_base + kColZ + s * 8;
         // hi class (q * 2^-20): k-steps 2, 3 of each 64-k half; the first MMA of a unit overwrites D
         ptx::umma_f16_ts(d, a + 16, b0 + 4, idesc, 0u);
         ptx::umma_f16_ts(d, a + 24, b0 + 6, idesc, 1u);
@@ -203,11 +295,11 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
         ptx::umma_f16_ts(d, a + 8, b0 + 2, idesc, 1u);
         ptx::umma_f16_ts(d, a + 32, b1 + 0, idesc, 1u);
         ptx::umma_f16_ts(d, a + 40, b1 + 2, idesc, 1u);
-        // D2 = ones . x^T: the sum of the group's activations, for the zero-point term
+        // zero point: D -= z * sum_k x_k (the same 8 columns of -z * 2^-24 against every k-step of the slice)
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) ptx::umma_f16_ts(d2, ones, b0 + (uint64_t)(kk * 2), idesc, kk != 0 ? 1u : 0u);
+        for (int kk = 0; kk < 4; kk++) ptx::umma_f16_ts(d, zc, b0 + (uint64_t)(kk * 2), idesc, 1u);
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) ptx::umma_f16_ts(d2, ones, b1 + (uint64_t)(kk * 2), idesc, 1u);
+        for (int kk = 0; kk < 4; kk++) ptx::umma_f16_ts(d, zc, b1 + (uint64_t)(kk * 2), idesc, 1u);
         ptx::tc_commit(bar(BAR_DONE + s));                         // A slot s free, D[s] / D2[s] complete
         ptx::tc_commit(bar(BAR_EMPTY_X + xp.st));                  // activation slot consumed
       }
@@ -220,33 +312,27 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
     const int nl = q * 32 + lane;         // weight column inside the tile == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t k_w = smem_base + kWBase + (uint32_t)nl * 16u, k_sz = smem_base + kWBase + kStageWBytes + (uint32_t)nl * 4u,
-             k_ta = lane_base + kColA + s * 64, k_d = lane_base + kColD + s * kNB, k_d2 = lane_base + kColD2 + s * kNB,
+             k_ta = lane_base + kColA + s * 64, k_d = lane_base + kColD + s * kNB, k_z = lane_base + kColZ + s * 8,
              k_fa = bar(BAR_FULL_A + s), k_dn = bar(BAR_DONE + s), k_fw = bar(BAR_FULL_W), k_ew = bar(BAR_EMPTY_W);
     // loop invariants through a self-shuffle: ptxas otherwise re-derives them from %tid in every iteration
     k_w = __shfl_sync(0xffffffffu, k_w, lane); k_sz = __shfl_sync(0xffffffffu, k_sz, lane);
     k_ta = __shfl_sync(0xffffffffu, k_ta, lane); k_d = __shfl_sync(0xffffffffu, k_d, lane);
-    k_d2 = __shfl_sync(0xffffffffu, k_d2, lane); k_fa = __shfl_sync(0xffffffffu, k_fa, lane);
+    k_z = __shfl_sync(0xffffffffu, k_z, lane); k_fa = __shfl_sync(0xffffffffu, k_fa, lane);
     k_dn = __shfl_sync(0xffffffffu, k_dn, lane); k_fw = __shfl_sync(0xffffffffu, k_fw, lane);
     k_ew = __shfl_sync(0xffffffffu, k_ew, lane);
-    if (s == 0) {
-      // the constant ones operand (this group's first full_A arrival orders it before the first MMA)
-      uint32_t o8[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) o8[i] = 0x3C003C00u;
-      ptx::tmem_st_x8(lane_base + kColOnes, o8);
-    }
     RingPos wp{s, 0};                     // this group's next unit is local unit s: ring stage s
     uint32_t dpar = 0;                    // parity of BAR_DONE[s]
     bool pending = false;                 // a unit of this group is in the tensor core: D[s] not accumulated yet
-    float sc_prev = 0.f, zs_prev = 0.f;   // its s * 2^24 and -s * z
+    float sc_prev = 0.f;                  // its scale * 2^24
     float acc[R];
 #pragma unroll
     for (int r = 0; r < R; r++) acc[r] = 0.f;
     bool dep_waited = false;
+    bool tl_first = true;
     u32 lbase = 0;                        // local index of the segment's first unit
     int seg = 0;
     SegIter si;
-    si.init(u0, u1, upt, n_tiles);
+    si.init_fd(u0, u1, p.fd_upt, p.fd_tiles);
     Seg sg;
 
     // Fold the finished unit of this group into the running sums (warp-collective).  Returning from the wait also
@@ -257,15 +343,11 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       ptx::tc_fence_after();
     };
     auto fold = [&]() {
-      uint32_t dv[R], ev[R];
+      uint32_t dv[R];
       tmem_ld_rows<R>(k_d, dv);
-      tmem_ld_rows<R>(k_d2, ev);
       ptx::tmem_wait_ld();
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        acc[r] = fmaf(sc_prev, __uint_as_float(dv[r]), acc[r]);
-        acc[r] = fmaf(zs_prev, __uint_as_float(ev[r]), acc[r]);
-      }
+      for (int r = 0; r < R; r++) acc[r] = fmaf(sc_prev, __uint_as_float(dv[r]), acc[r]);
     };
     // one 64-k half: two LDS.128 -> 16 lo-class + 16 hi-class half2 registers
     auto convert_half = [&](const uint4 &wa, const uint4 &wb, uint32_t (&lo)[16], uint32_t (&hi)[16]) {
@@ -282,6 +364,15 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
 
     while (si.next(sg, upt, n_tiles)) {
       const int n_seg = sg.r1 - sg.r0;
+      // Contributors of this tile, resolved while the first stage of the segment is still in flight.  A tile cut
+      // by CTA range boundaries has contributors c_first .. c_last (consecutive CTAs); c_first owns it.
+      const bool whole = (sg.r0 == 0 && sg.r1 == upt);           // this CTA covers the whole tile
+      int c_first = cta, c_last = cta;
+      if (!whole) {
+        const u32 tile_u0 = (u32)(sg.blk * n_tiles + sg.tile) * (u32)upt;
+        c_first = cta_of_unit_fd(tile_u0, p.fd_units, p.fd_grid);
+        c_last = cta_of_unit_fd(tile_u0 + upt - 1, p.fd_units, p.fd_grid);
+      }
       // units of this segment that fall to this group: local indices lbase + j with parity s
       int mine = 0;
       {
@@ -293,6 +384,7 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       for (; mine > 0; mine--) {
         const uint32_t stage_off = (uint32_t)wp.st * kStageBytes;
         ptx::mbar_wait(k_fw + wp.st * 8, wp.par);
+        if (tl_first) { FB2_TL(3); tl_first = false; }
         const uint32_t sz = ptx::lds32(k_sz + stage_off);
         uint4 wa = ptx::lds128(k_w + stage_off);
         uint4 wb = ptx::lds128(k_w + stage_off + 2048u);
@@ -303,7 +395,14 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
         if (pending) wait_done();                                 // MMAs of this group's previous unit are complete
         ptx::tmem_st_x16(k_ta, lo);
         ptx::tmem_st_x16(k_ta + 16, hi);
-        if (pending) fold();                                      // D[s] / D2[s] are read before the next MMAs overwrite them
+        {
+          // zero point of this unit: (1024 + z) as fp16 is 0x6400 + z, so 0x8000 | z == -z * 2^-24 is one add
+          const uint32_t zh = (sz >> 16) + 0x1C00u;
+          const uint32_t zp = zh | (zh << 16);
+          const uint32_t z8[8] = {zp, zp, zp, zp, zp, zp, zp, zp};
+          ptx::tmem_st_x8(k_z, z8);
+        }
+        if (pending) fold();                                      // D[s] is read before the next MMAs overwrite it
         convert_half(wa, wb, lo, hi);
         // the packed words are in registers: release the weight stage to the HBM stream
         if (lane == 0) ptx::mbar_arrive_after(k_ew + wp.st * 8, lo[15] ^ hi[15]);
@@ -313,27 +412,26 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
         ptx::tc_fence_before();
         if (lane == 0) ptx::mbar_arrive(k_fa);
         __syncwarp();
-        const float sf = __half2float(__ushort_as_half((unsigned short)(sz & 0xFFFF)));
-        const float zf = __half2float(__ushort_as_half((unsigned short)(sz >> 16))) - 1024.0f;
-        sc_prev = sf * 16777216.0f;
-        zs_prev = -sf * zf;
+        sc_prev = __half2float(__ushort_as_half((unsigned short)(sz & 0xFFFF))) * 16777216.0f;
         pending = true;
         wp.st += 2;
         if (wp.st >= SW) { wp.st -= SW; wp.par ^= 1u; }
       }
 
       // ------------------------------------------------ epilogue of this tile segment
+      FB2_TL(4);
       if (pending) {
         wait_done();
         fold();
         ptx::tc_fence_before();
         pending = false;
       }
+      FB2_TL(5);
       if (!dep_waited) {                  // before the first global write / scratch access
         ptx::grid_dependency_wait();
         dep_waited = true;
+        FB2_TL(2);
       }
-      const int r_begin = sg.r0, r_end = sg.r1;
       const int blk = sg.blk, tile = sg.tile, tau = sg.blk * n_tiles + sg.tile;
       const int nv = min(kNB, p.rm.m - blk * kNB);               // real rows of the block (dense)
       // the two groups swap the rows the other one finishes
@@ -362,17 +460,12 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       constexpr int kPart = kNB * kTileN;
       const int col = tile * kTileN + nl;
       const float bias = p.w.bias ? p.w.bias[col] : 0.0f;
-      const bool whole = (r_begin == 0 && r_end == upt);         // this CTA covered the whole tile
       const size_t push_off = push_world(p) ? ((size_t)(*(volatile const uint32_t *)p.push.epoch & 1u) * p.push.world +
                                               p.push.rank) * p.push.slot_elems : 0;
-      int c_first = cta, c_last = cta;
-      if (!whole) {
-        const u32 tile_u0 = (u32)tau * (u32)upt;
-        c_first = cta_of_unit(tile_u0, T, G);
-        c_last = cta_of_unit(tile_u0 + upt - 1, T, G);
-      }
       const bool owner = !whole && cta == c_first;
-      const bool ll = !whole && nv <= kLlRows && R <= kLlRows && G <= p.ll_ctas;
+      // flag-in-value exchange for every decode block: the slot area of a CTA, [2 accumulators][8 rows][128], holds
+      // the 16 rows of the one accumulator this kernel has
+      const bool ll = !whole && G <= p.ll_ctas;
       const int nr = nv - rb;                                    // real rows among this group's: j < nr
       auto store_out = [&](int row_in_block, float val) {
         const int cr = blk * kNB + row_in_block;
@@ -388,51 +481,92 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
         for (int j = 0; j < OWN; j++)
           if (j < nr) store_out(rb + j, v[j]);
       } else if (ll) {
-        // ---- flag-in-value exchange (tc_gemm.cu): only the real rows travel, no counter, no fence
-        auto slot_of = [&](int c, int j) { return p.ll + (size_t)c * kLlFloatsPerCta + (size_t)((rb + j) * kTileN + nl); };
+        // ---- flag-in-value exchange (protocol: tc_gemm.cu).  Slot layout of this kernel: [cta][16 / VW][column][VW], so
+        // the OWN rows of a thread are ONE vector store for the contributor and one vector load per contributor
+        // for the owner (element-wise relaxed.gpu accesses do not pipeline: four scalar stores cost a contributor
+        // 0.6 us).  Rows >= nv carry whatever the accumulator columns held: they are published, summed and reset
+        // like real ones (never stored to y), which keeps the vectors whole.
+#ifdef FB2_LL_SCALAR
+        constexpr int VW = 1;
+#else
+        constexpr int VW = OWN < 4 ? OWN : 4;                    // vector width
+#endif
+        constexpr int NV = OWN / VW;                             // vectors per thread and contributor
+        auto slot_of = [&](int c, int vi) {      // [cta][row chunk of VW rows][column nl][VW]: a warp's vectors are contiguous
+          return p.ll + (size_t)c * kLlFloatsPerCta + (size_t)(((rb / VW + vi) * kTileN + nl) * VW);
+        };
         if (!owner) {
 #pragma unroll
-          for (int j = 0; j < OWN; j++)
-            if (j < nr) {
-              const uint32_t u = __float_as_uint(v[j]);
-              ptx::st_relaxed_u32(slot_of(cta, j), u == kLlEmpty ? 0x7fffffffu : u);
+          for (int vi = 0; vi < NV; vi++) {
+            uint32_t u[VW];
+#pragma unroll
+            for (int e = 0; e < VW; e++) {
+              u[e] = __float_as_uint(v[vi * VW + e]);
+              if (u[e] == kLlEmpty) u[e] = 0x7fffffffu;
             }
+            st_slots<VW>(slot_of(cta, vi), u);
+          }
         } else {
-          constexpr int UB = 8;                                  // contributors polled together
+          constexpr int UB = 32 / OWN < 8 ? 32 / OWN : 8;        // contributors polled together (<= 32 registers)
 #pragma unroll 1
           for (int c0 = c_first + 1; c0 <= c_last; c0 += UB) {
-            uint32_t t[UB][OWN];
+            uint32_t t[UB][NV][VW];
 #pragma unroll
             for (int i = 0; i < UB; i++)
 #pragma unroll
-              for (int j = 0; j < OWN; j++)
-                t[i][j] = (j < nr && c0 + i <= c_last) ? ptx::ld_relaxed_u32(slot_of(c0 + i, j)) : 0u;
+              for (int vi = 0; vi < NV; vi++) {
+                if (c0 + i <= c_last) {
+                  ld_slots<VW>(slot_of(c0 + i, vi), t[i][vi]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < VW; e++) t[i][vi][e] = 0u;
+                }
+              }
 #ifdef FB2_WAIT_TIMEOUT
             const long long t0 = clock64();
 #endif
+#ifdef FB2_TRACE
+            int rounds = 0;
+#endif
             for (;;) {
+              // all slots are tested first and all missing vectors re-requested together
               bool waiting = false;
 #pragma unroll
               for (int i = 0; i < UB; i++)
 #pragma unroll
-                for (int j = 0; j < OWN; j++) waiting |= t[i][j] == kLlEmpty;
+                for (int vi = 0; vi < NV; vi++)
+#pragma unroll
+                  for (int e = 0; e < VW; e++) waiting |= t[i][vi][e] == kLlEmpty;
               if (!waiting) break;
+#ifdef FB2_TRACE
+              rounds++;
+#endif
 #pragma unroll
               for (int i = 0; i < UB; i++)
 #pragma unroll
-                for (int j = 0; j < OWN; j++)
-                  if (t[i][j] == kLlEmpty) t[i][j] = ptx::ld_relaxed_u32(slot_of(c0 + i, j));
+                for (int vi = 0; vi < NV; vi++) {
+                  bool miss = false;
+#pragma unroll
+                  for (int e = 0; e < VW; e++) miss |= t[i][vi][e] == kLlEmpty;
+                  if (miss) ld_slots<VW>(slot_of(c0 + i, vi), t[i][vi]);   // only ever true for vectors that were requested
+                }
 #ifdef FB2_WAIT_TIMEOUT
               if (clock64() - t0 > 4000000000LL) { printf("fb2: ll slot wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
 #endif
             }
+            FB2_TL(9);
+#ifdef FB2_TRACE
+            FB2_TLV(15, rounds);
+#endif
 #pragma unroll
             for (int i = 0; i < UB; i++)
 #pragma unroll
-              for (int j = 0; j < OWN; j++)
-                if (j < nr && c0 + i <= c_last) {
-                  v[j] += __uint_as_float(t[i][j]);
-                  ptx::st_relaxed_u32(slot_of(c0 + i, j), kLlEmpty);   // consumed: empty again for the next launch
+              for (int vi = 0; vi < NV; vi++)
+                if (c0 + i <= c_last) {
+#pragma unroll
+                  for (int e = 0; e < VW; e++) v[vi * VW + e] += __uint_as_float(t[i][vi][e]);
+                  // consumed: empty again for the next launch (a plain store: the kernel boundary publishes it)
+                  reset_slots<VW>(slot_of(c0 + i, vi));
                 }
           }
 #pragma unroll
@@ -479,6 +613,7 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
         }
       }
     }
+    FB2_TL(6);
     if (push_world(p)) {
       // every participating CTA signals every rank once: its pushed tiles are complete
       ptx::named_bar_sync(1, kDequantWarps * 32);
@@ -495,12 +630,13 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == kWarpMma) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  FB2_TL(7);
 }
 
-template <int R, bool kPush>
+template <int R, bool kPush, bool kGather>
 __global__ void __launch_bounds__(384, 2) dk_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
   ptx::launch_dependents();
-  dk_body<R, kPush>(p, &xmap);
+  dk_body<R, kPush, kGather>(p, &xmap);
 }
 
 }  // namespace dk

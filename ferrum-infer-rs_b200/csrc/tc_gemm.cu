@@ -114,6 +114,9 @@ struct TcParams {
   int ld_out;             // output row stride
   int x_tma;              // activations come through the 2-D tensor map (dense / dispatch rows)
   int whole_tiles;        // dense / dispatch rows: CTA ranges are cut on tile boundaries (host decision)
+  sched::FastDiv fd_grid, fd_upt, fd_tiles, fd_units;   // decode kernel: divisions by launch constants (sched.cuh)
+  int w_stages;           // decode kernel: weight ring depth
+  int l2_prefetch;        // decode kernel: every CTA requests its whole range into L2 at entry
   PushTargets push;       // row-parallel linear: output tiles are pushed to every rank's receive slot
 };
 
@@ -236,12 +239,16 @@ __device__ __forceinline__ long long fb2_gtime() { long long t; asm volatile("mo
     *((volatile long long *)g_trace + (size_t)(296 + (((p.x_tma >> 16) & 7) * 296 + blockIdx.x)) * 32 + (slot)) = fb2_gtime(); } } while (0)
 #define FB2_TLV(slot, v) do { if (g_trace && threadIdx.x == 0) { \
     *((volatile long long *)g_trace + (size_t)(296 + (((p.x_tma >> 16) & 7) * 296 + blockIdx.x)) * 32 + (slot)) = (long long)(v); } } while (0)
+// same, by lane 0 of whichever warp executes it
+#define FB2_TLW(slot) do { if (g_trace && (threadIdx.x & 31) == 0) { \
+    *((volatile long long *)g_trace + (size_t)(296 + (((p.x_tma >> 16) & 7) * 296 + blockIdx.x)) * 32 + (slot)) = fb2_gtime(); } } while (0)
 #else
 #define FB2_MARK(v) do { } while (0)
 #define FB2_MARK2(slot, v) do { } while (0)
 #define FB2_TSTAMP(slot) do { } while (0)
 #define FB2_TL(slot) do { } while (0)
 #define FB2_TLV(slot, v) do { } while (0)
+#define FB2_TLW(slot) do { } while (0)
 #endif
 
 // kPush instantiations (row-parallel decode GEMMs with the fused all-reduce) are separate kernels: the
@@ -1026,25 +1033,26 @@ int launch_plain(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const
   FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NB, kSilu, kPush>, p, xmap));
   return FB2_OK;
 }
-// decode-batch kernel (tc_decode.cuh): dense rows, <= 16 of them, activations through the tensor map
-template <int R, bool kPush>
+// decode-batch kernel (tc_decode.cuh): dense rows, activations through the tensor map, or (kGather) act-order
+// layers whose rows fit in shared memory: gathered inside the kernel
+template <int R, bool kPush, bool kGather>
 int launch_dk(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
-  static const cudaError_t attr_rc =
-      cudaFuncSetAttribute(dk::dk_gemm_kernel<R, kPush>, cudaFuncAttributeMaxDynamicSharedMemorySize, dk::kSmemBytes);
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(dk::dk_gemm_kernel<R, kPush, kGather>,
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, dk::kSmemBudget);
   FB2_CUDA_TRY(attr_rc);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   launch_cfg(cfg, attr, pl, stream);
-  cfg.dynamicSmemBytes = dk::kSmemBytes;
-  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, dk::dk_gemm_kernel<R, kPush>, p, xmap));
+  cfg.dynamicSmemBytes = dk::kSmemBudget;
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, dk::dk_gemm_kernel<R, kPush, kGather>, p, xmap));
   return FB2_OK;
 }
-template <bool kPush>
+template <bool kPush, bool kGather>
 int launch_dk_rows(int m, const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
-  return m <= 1 ? launch_dk<1, kPush>(pl, stream, p, xmap)
-         : m <= 2 ? launch_dk<2, kPush>(pl, stream, p, xmap)
-         : m <= 4 ? launch_dk<4, kPush>(pl, stream, p, xmap)
-         : m <= 8 ? launch_dk<8, kPush>(pl, stream, p, xmap) : launch_dk<16, kPush>(pl, stream, p, xmap);
+  return m <= 1 ? launch_dk<1, kPush, kGather>(pl, stream, p, xmap)
+         : m <= 2 ? launch_dk<2, kPush, kGather>(pl, stream, p, xmap)
+         : m <= 4 ? launch_dk<4, kPush, kGather>(pl, stream, p, xmap)
+         : m <= 8 ? launch_dk<8, kPush, kGather>(pl, stream, p, xmap) : launch_dk<16, kPush, kGather>(pl, stream, p, xmap);
 }
 
 template <int NB>
@@ -1059,6 +1067,19 @@ int launch_dispatch(const TcPlan &pl, cudaStream_t stream, const TcParams &p, co
 }
 
 }  // namespace
+
+// The decode kernel (tc_decode.cuh) serves dense launches of at most 8 rows.
+static bool dk_eligible(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue) {
+  static const bool no_dk = [] { const char *e = getenv("FB2_DEBUG_NO_DK"); return e && e[0] == '1'; }();
+  static const int max_m = [] { const char *e = getenv("FB2_DEBUG_DK_MAXM"); return e ? atoi(e) : 8; }();
+  return !no_dk && rows.mode == ROWS_DENSE && rows.m >= 1 && rows.m <= max_m && rows.m <= 16 && !epilogue && !tbl;
+}
+// ... and gathers act-order activations itself when the m rows of x fit next to a weight ring of kMinWStages
+bool dk_gather_ok(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue) {
+  static const bool no_gather = [] { const char *e = getenv("FB2_DEBUG_NO_DK_GATHER"); return e && e[0] == '1'; }();
+  return !no_gather && w.perm && dk_eligible(w, rows, tbl, epilogue) && w.k % 8 == 0 &&
+         dk::w_stages_for(rows.m * w.k * 2) >= dk::kMinWStages;
+}
 
 bool tc_supported(const WeightRef &w) {
   return w.tiles != nullptr && w.group_size == kGroup && w.k % kGroup == 0 && w.n % kTileN == 0 &&
@@ -1182,7 +1203,13 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   CUtensorMap xmap;
   memset(&xmap, 0, sizeof(xmap));
   p.x_tma = 0;
-  if (rows.mode != ROWS_ROUTED && x_rows > 0 && ((uintptr_t)x % 16) == 0) {
+  if (w.perm) {
+    // act-order gather inside the decode kernel (run_tc only leaves perm set when dk_gather_ok said so)
+    if (!dk_gather_ok(w, rows, tbl, epilogue) || ((uintptr_t)x % 16) != 0) {
+      set_error("internal: act-order activations must be gathered before this launch");
+      return FB2_ERR_ARG;
+    }
+  } else if (rows.mode != ROWS_ROUTED && x_rows > 0 && ((uintptr_t)x % 16) == 0) {
     int rc = make_x_tensor_map(&xmap, x, x_rows, (size_t)w.k, nb);
     if (rc) return rc;
     p.x_tma = 1;
@@ -1206,11 +1233,22 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   }
 #endif
   int rc;
-  static const bool no_dk = [] { const char *e = getenv("FB2_DEBUG_NO_DK"); return e && e[0] == '1'; }();
-  const bool use_dk = !no_dk && rows.mode == ROWS_DENSE && nb == 16 && !epilogue && !tbl && (p.x_tma & 1);
+  const bool use_dk = dk_eligible(w, rows, tbl, epilogue) && ((p.x_tma & 1) || w.perm);
   if (use_dk) {
-    rc = (push && push->world) ? launch_dk_rows<true>(rows.m, pl, stream, p, xmap)
-                               : launch_dk_rows<false>(rows.m, pl, stream, p, xmap);
+    static const bool l2pf = [] { const char *e = getenv("FB2_DEBUG_L2PF"); return e && e[0] == '1'; }();
+    p.l2_prefetch = l2pf ? 1 : 0;
+    p.fd_grid = make_fastdiv((u32)pl.grid);
+    p.fd_upt = make_fastdiv((u32)p.groups);
+    p.fd_tiles = make_fastdiv((u32)pl.n_tiles);
+    p.fd_units = make_fastdiv((u32)pl.units);
+    const bool pushing = push && push->world;
+    if (w.perm) {
+      p.w_stages = dk::w_stages_for(rows.m * w.k * 2);
+      rc = pushing ? launch_dk_rows<true, true>(rows.m, pl, stream, p, xmap) : launch_dk_rows<false, true>(rows.m, pl, stream, p, xmap);
+    } else {
+      p.w_stages = dk::w_stages_for(0);
+      rc = pushing ? launch_dk_rows<true, false>(rows.m, pl, stream, p, xmap) : launch_dk_rows<false, false>(rows.m, pl, stream, p, xmap);
+    }
   } else if (push && push->world) {
     if (tbl || epilogue || nb > 64) {
       set_error("fused all-reduce: decode-sized dense launches only (<= 64 rows per block)");

@@ -26,4 +26,9 @@ for (name, k, n) in bench.LLAMA["linears"]:
         b = bench.alg_bytes(k, n, m, act) * layers
         out[f"{name} M={m}"] = (round(t * 1e3 / layers, 2), round(b / (t * 1e-3) / 1e9))
     del lins
+import subprocess
+try:
+    print("clocks:", subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,temperature.gpu", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip())
+except Exception as e:
+    print("clocks: n/a", e)
 print(f"act={act} pdl={os.environ.get('FB2_DEBUG_NO_PDL','0')!='1'}", out)
