@@ -385,7 +385,7 @@ static int reserve_scratch_for(const WeightRef &w, int device, size_t rows) {
 // pregrow_marlin_gather_scratch, capabilities.rs:205-214).
 static int run_tc(const WeightRef &w_in, const RowMap &rm, const DispatchTable *tbl, const __half *x,
                   size_t x_rows, __half *y, int epilogue, int device, cudaStream_t stream,
-                  const PushTargets *push = nullptr) {
+                  const PushTargets *push = nullptr, int dk_flags = 0, const int32_t *out_map = nullptr) {
   int sms = 0;
   TcScratch sc = current_scratch(device, &sms);
   size_t pb = 0, nc = 0;
@@ -423,7 +423,7 @@ static int run_tc(const WeightRef &w_in, const RowMap &rm, const DispatchTable *
     x = xp;
     w.perm = nullptr;
   }
-  return launch_tc_gemm(w, rm, tbl, x, x_rows, y, epilogue, sc, sms, stream, push);
+  return launch_tc_gemm(w, rm, tbl, x, x_rows, y, epilogue, sc, sms, stream, push, dk_flags, out_map);
 }
 
 // Registry of live weights per device so that fb2_pregrow_scratch can size the pool for
@@ -837,6 +837,12 @@ int fb2_gptq_stack_create(const int32_t *const *qweights, const float *const *sc
     if (ing.act_order) {
       if ((rc = upload(&d_perm, ing.perm.data(), k))) return fail(rc);
       st->allocs.push_back(d_perm);
+      std::vector<int32_t> inv(k);
+      for (size_t i = 0; i < k; i++) inv[ing.perm[i]] = (int32_t)i;
+      int32_t *d_inv = nullptr;
+      if ((rc = upload(&d_inv, inv.data(), k))) return fail(rc);
+      st->allocs.push_back(d_inv);
+      w.inv_perm = d_inv;
     }
     const size_t per_expert = tile_bytes(k, n_per_expert);
     uint8_t *tiles = nullptr;
@@ -1027,7 +1033,8 @@ int fb2_gptq_stack_gemm_batched(const fb2_stack_t *st, fb2_stream_t stream, cons
 static int routed_gemm(const fb2_stack_t *st, fb2_stream_t stream, const fb2_half *x,
                        const int32_t *sorted_token_ids, const int32_t *expert_ids,
                        const int32_t *num_tokens_post_padded, fb2_half *y, size_t prob_m,
-                       size_t block, size_t top_k, size_t sorted_capacity, int epilogue) {
+                       size_t block, size_t top_k, size_t sorted_capacity, int epilogue, int dk_flags = 0,
+                       const int32_t *out_map = nullptr, bool x_is_sorted = false) {
   if (!st) { set_error("stack handle is NULL"); return FB2_ERR_ARG; }
   if (prob_m == 0) return FB2_OK;
   if (!x || !y || !sorted_token_ids || !expert_ids || !num_tokens_post_padded) {
@@ -1055,8 +1062,13 @@ static int routed_gemm(const fb2_stack_t *st, fb2_stream_t stream, const fb2_hal
   rm.max_blocks = bound;
   if (bound <= 0) return FB2_OK;
   const bool tc = tc_supported(st->w) && (!epilogue || (st->w.n / 2) % kTileN == 0);
-  if (tc) return run_tc(st->w, rm, nullptr, (const __half *)x, prob_m, (__half *)y, epilogue, st->device,
-                        (cudaStream_t)stream);
+  if (tc) {
+    WeightRef w = st->w;
+    if (x_is_sorted) w.perm = nullptr;         // the caller delivers the activations in this stack's sorted-k order
+    return run_tc(w, rm, nullptr, (const __half *)x, prob_m, (__half *)y, epilogue, st->device, (cudaStream_t)stream,
+                  nullptr, dk_flags, out_map);
+  }
+  if (x_is_sorted || out_map) { set_error("internal: fused act-order FFN needs the tiled weight format"); return FB2_ERR_ARG; }
   return launch_generic_gemm(st->w, rm, (const __half *)x, (__half *)y, epilogue, (cudaStream_t)stream);
 }
 
@@ -1154,7 +1166,7 @@ int fb2_fused_gelu_tanh_mul_split(fb2_stream_t stream, const fb2_half *gate_up, 
 //   total [1] i32 | act [pairs, I] f16 | down [pairs, H] f16
 constexpr size_t kFfnBlock = 16;
 struct FfnLayout {
-  size_t ids, wts, sorted, block_ids, total, act, down, bytes, cap;
+  size_t ids, wts, sorted, block_ids, total, act, down, xperm, bytes, cap;
 };
 static FfnLayout ffn_layout(size_t batch, size_t top_k, size_t num_experts, size_t inter, size_t hidden) {
   FfnLayout L;
@@ -1168,6 +1180,7 @@ static FfnLayout ffn_layout(size_t batch, size_t top_k, size_t num_experts, size
   L.total = off; off = align256(off + 4);
   L.act = off; off = align256(off + pairs * inter * 2);
   L.down = off; off = align256(off + pairs * hidden * 2);
+  L.xperm = off; off = align256(off + batch * hidden * 2);      // act-order gate|up stack: x in its sorted-k order
   L.bytes = off;
   return L;
 }
@@ -1206,25 +1219,48 @@ int fb2_moe_ffn_forward(const fb2_stack_t *gate_up, const fb2_stack_t *down, fb2
   fb2_half *act = (fb2_half *)(ws + L.act);
   fb2_half *dn = (fb2_half *)(ws + L.down);
   const size_t pairs = batch * top_k;
+  // Decode batches (on average <= 2 pairs per expert): blocks of 8 rows, served by the decode kernel.  The pair of
+  // grouped GEMMs is then chained: the gate|up kernel releases its dependents only after its own grid dependency
+  // has resolved (the routing arrays are complete by then), so the down kernel may plan and stream its weights
+  // without waiting for the gate|up kernel to finish.
+  const size_t block = pairs <= 2 * E ? 8 : kFfnBlock;
+  bool chained = false;
+  {
+    RowMap rm{};
+    rm.mode = ROWS_ROUTED;
+    rm.block = (int)block;
+    chained = tc_supported(gate_up->w) && tc_supported(down->w) && (gate_up->w.n / 2) % kTileN == 0 &&
+              dk_routed_ok(gate_up->w, rm, 1) && dk_routed_ok(down->w, rm, 0);
+  }
   int rc;
-  if (route_align_small_supported((int)batch, (int)E, (int)top_k)) {
-    // 1+2 for decode batches: routing and block alignment in one single-CTA launch
+  // Act-order stacks in the chained form need no gather launch of their own: the routing launch also gathers x into
+  // the gate|up stack's sorted-k order (CTAs 1..batch), and the gate|up epilogue stores act[:, c] at the column the
+  // down stack's order wants (its inverse permutation), so the down GEMM reads act as it lies.
+  const bool small_route = route_align_small_supported((int)batch, (int)E, (int)top_k);
+  const bool fuse_x = chained && small_route && gate_up->w.perm != nullptr;
+  const bool fuse_act = chained && down->w.perm != nullptr && down->w.inv_perm != nullptr;
+  const fb2_half *x_gu = x;
+  if (small_route) {
+    // 1+2 for decode batches: routing and block alignment in one launch
     FB2_CUDA_TRY(cudaSetDevice(gate_up->device));
+    __half *xp = fuse_x ? (__half *)(ws + L.xperm) : nullptr;
     if ((rc = launch_route_align_small((const __half *)router_logits, ids, wts, sorted, block_ids, total, (int)batch,
-                                       (int)E, (int)top_k, norm_topk_prob, kFfnBlock, (int)L.cap,
-                                       (cudaStream_t)stream))) return rc;
+                                       (int)E, (int)top_k, norm_topk_prob, (int)block, (int)L.cap,
+                                       (cudaStream_t)stream, fuse_x ? (const __half *)x : nullptr,
+                                       fuse_x ? gate_up->w.perm : nullptr, xp, (int)hidden))) return rc;
+    if (fuse_x) x_gu = (const fb2_half *)xp;
   } else {
     // 1. route (dispatch.rs:1645)
     if ((rc = fb2_moe_route_topk_softmax(stream, router_logits, ids, wts, batch, E, top_k, norm_topk_prob))) return rc;
     // 2. align with pair ids: A row = id / top_k (gather fused), C row = id (dispatch.rs:1998-2009)
-    if ((rc = fb2_moe_align_block_size(stream, ids, sorted, block_ids, total, pairs, E, kFfnBlock, L.cap, 1))) return rc;
+    if ((rc = fb2_moe_align_block_size(stream, ids, sorted, block_ids, total, pairs, E, block, L.cap, 1))) return rc;
   }
   // 3+4. gate-up grouped GEMM with SwiGLU epilogue -> act [pairs, I]
-  if ((rc = fb2_gptq_stack_gemm_routed_silu(gate_up, stream, x, sorted, block_ids, total, act, batch,
-                                            kFfnBlock, top_k, L.cap))) return rc;
+  if ((rc = routed_gemm(gate_up, stream, x_gu, sorted, block_ids, total, act, batch, block, top_k, L.cap, 1,
+                        chained ? DK_FLAG_LATE_TRIGGER : 0, fuse_act ? down->w.inv_perm : nullptr, fuse_x))) return rc;
   // 5. down grouped GEMM: rows are pair ids on both sides (prob_m = pairs, top_k = 1)
-  if ((rc = fb2_gptq_stack_gemm_routed(down, stream, act, sorted, block_ids, total, dn, pairs,
-                                       kFfnBlock, 1, L.cap))) return rc;
+  if ((rc = routed_gemm(down, stream, act, sorted, block_ids, total, dn, pairs, block, 1, L.cap, 0,
+                        chained ? DK_FLAG_META_EARLY : 0, nullptr, fuse_act))) return rc;
   // 6. combine: dense [batch, top_k, hidden] weighted sum (dispatch.rs:2147-2159)
   return fb2_moe_weighted_sum_batched(stream, dn, wts, out, batch, top_k, hidden);
 }

@@ -102,6 +102,7 @@ struct WeightRef {
   // tiled format (fast path); null when the layer only has the raw format
   const uint8_t *tiles;              // [experts][n_tiles_total][groups][kStageBytes]
   const int32_t *perm;               // [K] sorted position -> disk row, or null
+  const int32_t *inv_perm;           // [K] disk row -> sorted position (stacks only; a producer's column map), or null
   // raw format (generic path)
   const int32_t *qweight;            // [experts][K/8][ld]
   const __half *scales;              // [experts][G][ld]
@@ -132,9 +133,11 @@ int launch_route_topk_softmax(const __half *logits, int32_t *ids, float *wts, in
                               int num_experts, int top_k, int norm, cudaStream_t stream);
 // routing + block alignment (pair ids) of a decode batch in one single-CTA launch
 bool route_align_small_supported(int batch, int num_experts, int top_k);
+// x / perm / xp non-null: CTAs 1..batch of the same launch also gather xp[r, j] = x[r, perm[j]] (act-order expert stacks)
 int launch_route_align_small(const __half *logits, int32_t *ids, float *wts, int32_t *sorted_ids,
                              int32_t *block_ids, int32_t *total_post_pad, int batch, int num_experts, int top_k,
-                             int norm, int block_size, int sorted_max, cudaStream_t stream);
+                             int norm, int block_size, int sorted_max, cudaStream_t stream,
+                             const __half *x = nullptr, const int32_t *perm = nullptr, __half *xp = nullptr, int hidden = 0);
 // expert parallelism, sender side: routing + dispatch plan in one launch; row scatter into the send buffer
 bool ep_route_plan_supported(int batch, int num_experts, int top_k, int world);
 int launch_ep_route_plan(const __half *logits, int32_t *ids, float *wts, int32_t *slot_of_pair, int32_t *send_meta,
@@ -183,6 +186,10 @@ constexpr size_t kLlBytes = (size_t)kLlMaxCtas * 2 * 8 * 128 * sizeof(uint32_t);
 bool tc_supported(const WeightRef &w);
 // act-order launches the decode kernel gathers itself (no permute launch, w.perm stays set)
 bool dk_gather_ok(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue);
+// routed launches the decode kernel serves (and therefore honours the DK_FLAG_* chain hints below)
+bool dk_routed_ok(const WeightRef &w, const RowMap &rows, int epilogue);
+constexpr int DK_FLAG_META_EARLY = 1;     // == dk::DKF_META_EARLY (tc_decode.cuh)
+constexpr int DK_FLAG_LATE_TRIGGER = 2;   // == dk::DKF_LATE_TRIGGER
 // Split-K scratch one launch with these rows needs (0 / 0 when it does not split).
 void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count,
                      size_t *partial_bytes, size_t *counters);
@@ -190,7 +197,8 @@ void tc_requirements(const WeightRef &w, const RowMap &rows, int epilogue, int s
 // x_rows: rows of x that may be addressed (bounds of the activation tensor map)
 int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, const __half *x,
                    size_t x_rows, __half *y, int epilogue, const TcScratch &scratch, int sm_count,
-                   cudaStream_t stream, const PushTargets *push = nullptr);
+                   cudaStream_t stream, const PushTargets *push = nullptr, int dk_flags = 0,
+                   const int32_t *out_map = nullptr);
 // CTAs the launch above uses (each signals the peers once when it pushes)
 int tc_grid_size(const WeightRef &w, const RowMap &rows, int epilogue, int sm_count);
 const char *tc_kernel_name(const WeightRef &w, size_t m);

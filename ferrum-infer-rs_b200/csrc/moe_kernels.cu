@@ -219,11 +219,20 @@ __global__ void __launch_bounds__(kRouteAlignThreads)
 route_align_small_kernel(const __half *__restrict__ logits, int32_t *__restrict__ out_ids, float *__restrict__ out_w,
                          int32_t *__restrict__ sorted_ids, int32_t *__restrict__ block_ids,
                          int32_t *__restrict__ total_post_pad, int batch, int num_experts, int top_k, int norm,
-                         int block_size, int sorted_max) {
+                         int block_size, int sorted_max, const __half *__restrict__ x, const int32_t *__restrict__ perm,
+                         __half *__restrict__ xp, int hidden) {
   extern __shared__ float s_probs[];                  // [32 warps][num_experts]
   __shared__ unsigned s_mask[kMaxExperts];            // tokens that selected expert e
   __shared__ int s_off[kMaxExperts + 1];              // padded start of expert e's run
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (blockIdx.x > 0) {
+    // act-order expert stack: CTA r + 1 gathers row r of the activations into sorted-k order while CTA 0 routes
+    // (reference: gather_columns.cu:15 -- a separate launch in front of every grouped GEMM)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int r = blockIdx.x - 1;
+    for (int j = threadIdx.x; j < hidden; j += kRouteAlignThreads) xp[(size_t)r * hidden + j] = x[(size_t)r * hidden + perm[j]];
+    return;
+  }
   for (int i = threadIdx.x; i < num_experts; i += kRouteAlignThreads) s_mask[i] = 0u;
   __syncthreads();
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -245,9 +254,20 @@ route_align_small_kernel(const __half *__restrict__ logits, int32_t *__restrict_
     __syncwarp();
     for (int i = lane; i < num_experts; i += 32) probs[i] = expf(probs[i] - tmax);
     __syncwarp();
+    // left to right, as router.rs:150-155 -- from registers: four independent shared-memory loads in flight per
+    // step instead of one dependent load per add (the serial form cost 2 us of a 128-expert row)
     float sum = 0.f;
-    if (lane == 0)
-      for (int i = 0; i < num_experts; i++) sum += probs[i];   // left to right, as router.rs:150-155
+    if (lane == 0) {
+      int i = 0;
+      for (; i + 8 <= num_experts; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = probs[i + j];
+#pragma unroll
+        for (int j = 0; j < 8; j++) sum += v[j];
+      }
+      for (; i < num_experts; i++) sum += probs[i];
+    }
     sum = __shfl_sync(0xffffffffu, sum, 0);
     const float inv = 1.0f / sum;
     for (int i = lane; i < num_experts; i += 32) probs[i] *= inv;
@@ -351,9 +371,20 @@ ep_route_plan_kernel(const __half *__restrict__ logits, int32_t *__restrict__ ou
     __syncwarp();
     for (int i = lane; i < num_experts; i += 32) probs[i] = expf(probs[i] - tmax);
     __syncwarp();
+    // left to right, as router.rs:150-155 -- from registers: four independent shared-memory loads in flight per
+    // step instead of one dependent load per add (the serial form cost 2 us of a 128-expert row)
     float sum = 0.f;
-    if (lane == 0)
-      for (int i = 0; i < num_experts; i++) sum += probs[i];   // left to right, as router.rs:150-155
+    if (lane == 0) {
+      int i = 0;
+      for (; i + 8 <= num_experts; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = probs[i + j];
+#pragma unroll
+        for (int j = 0; j < 8; j++) sum += v[j];
+      }
+      for (; i < num_experts; i++) sum += probs[i];
+    }
     sum = __shfl_sync(0xffffffffu, sum, 0);
     const float inv = 1.0f / sum;
     for (int i = lane; i < num_experts; i += 32) probs[i] *= inv;
@@ -474,12 +505,15 @@ bool route_align_small_supported(int batch, int num_experts, int top_k) {
 
 int launch_route_align_small(const __half *logits, int32_t *ids, float *wts, int32_t *sorted_ids,
                              int32_t *block_ids, int32_t *total_post_pad, int batch, int num_experts, int top_k,
-                             int norm, int block_size, int sorted_max, cudaStream_t stream) {
+                             int norm, int block_size, int sorted_max, cudaStream_t stream, const __half *x,
+                             const int32_t *perm, __half *xp, int hidden) {
   const size_t smem = (size_t)32 * num_experts * sizeof(float);
   if (smem > 48 * 1024)
     FB2_CUDA_TRY(cudaFuncSetAttribute(route_align_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  return launch_pdl(route_align_small_kernel, dim3(1), dim3(kRouteAlignThreads), smem, stream, logits, ids, wts,
-                    sorted_ids, block_ids, total_post_pad, batch, num_experts, top_k, norm, block_size, sorted_max);
+  const bool gather = x && perm && xp && hidden > 0;
+  return launch_pdl(route_align_small_kernel, dim3(gather ? 1 + batch : 1), dim3(kRouteAlignThreads), smem, stream, logits,
+                    ids, wts, sorted_ids, block_ids, total_post_pad, batch, num_experts, top_k, norm, block_size,
+                    sorted_max, x, perm, xp, hidden);
 }
 
 bool ep_route_plan_supported(int batch, int num_experts, int top_k, int world) {

@@ -120,7 +120,14 @@ FB2_HD GridPlan plan_grid(long long units, int upt, int slots, bool routed, bool
   if (tile_align && !gp.whole_tiles && !routed && nt > 0 && nt * 2 <= slots) {
     long long s = slots / nt;
     if (s > upt / 2) s = upt / 2;                                   // >= 2 units per CTA
-    if (s >= 1) gp.grid = (int)(nt * s);
+    if (s >= 1) {
+      // the slowest CTA of a tile streams ceil(upt / s) units: the smallest s that reaches the minimum has the
+      // fewest contributors per fix-up (o_proj: 8 CTAs x 4 units instead of 9 x 3..4) and leaves slots free for
+      // the next kernel's early CTAs
+      const long long best = (upt + s - 1) / s;
+      while (s > 1 && (upt + s - 2) / (s - 1) == best) s--;
+      gp.grid = (int)(nt * s);
+    }
   }
   return gp;
 }

@@ -115,6 +115,9 @@ struct TcParams {
   int x_tma;              // activations come through the 2-D tensor map (dense / dispatch rows)
   int whole_tiles;        // dense / dispatch rows: CTA ranges are cut on tile boundaries (host decision)
   sched::FastDiv fd_grid, fd_upt, fd_tiles, fd_units;   // decode kernel: divisions by launch constants (sched.cuh)
+  int dk_flags;           // decode kernel: DKF_* (tc_decode.cuh)
+  const int32_t *out_map; // decode kernel, routed: output column c is stored at out_map[c] (the act-order column order of
+                          // the consumer: no gather launch between the two grouped GEMMs of an FFN), or null
   int w_stages;           // decode kernel: weight ring depth
   int l2_prefetch;        // decode kernel: every CTA requests its whole range into L2 at entry
   PushTargets push;       // row-parallel linear: output tiles are pushed to every rank's receive slot
@@ -1033,26 +1036,26 @@ int launch_plain(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const
   FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NB, kSilu, kPush>, p, xmap));
   return FB2_OK;
 }
-// decode-batch kernel (tc_decode.cuh): dense rows, activations through the tensor map, or (kGather) act-order
-// layers whose rows fit in shared memory: gathered inside the kernel
-template <int R, bool kPush, bool kGather>
+// decode-batch kernel (tc_decode.cuh): dense rows through the tensor map, act-order rows gathered inside the kernel,
+// or routed blocks of an expert stack (with or without the SwiGLU epilogue)
+template <int R, int kMode, bool kSilu, bool kPush>
 int launch_dk(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
-  static const cudaError_t attr_rc = cudaFuncSetAttribute(dk::dk_gemm_kernel<R, kPush, kGather>,
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(dk::dk_gemm_kernel<R, kMode, kSilu, kPush>,
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, dk::kSmemBudget);
   FB2_CUDA_TRY(attr_rc);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   launch_cfg(cfg, attr, pl, stream);
   cfg.dynamicSmemBytes = dk::kSmemBudget;
-  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, dk::dk_gemm_kernel<R, kPush, kGather>, p, xmap));
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, dk::dk_gemm_kernel<R, kMode, kSilu, kPush>, p, xmap));
   return FB2_OK;
 }
-template <bool kPush, bool kGather>
+template <int kMode, bool kPush>
 int launch_dk_rows(int m, const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
-  return m <= 1 ? launch_dk<1, kPush, kGather>(pl, stream, p, xmap)
-         : m <= 2 ? launch_dk<2, kPush, kGather>(pl, stream, p, xmap)
-         : m <= 4 ? launch_dk<4, kPush, kGather>(pl, stream, p, xmap)
-         : m <= 8 ? launch_dk<8, kPush, kGather>(pl, stream, p, xmap) : launch_dk<16, kPush, kGather>(pl, stream, p, xmap);
+  return m <= 1 ? launch_dk<1, kMode, false, kPush>(pl, stream, p, xmap)
+         : m <= 2 ? launch_dk<2, kMode, false, kPush>(pl, stream, p, xmap)
+         : m <= 4 ? launch_dk<4, kMode, false, kPush>(pl, stream, p, xmap)
+         : m <= 8 ? launch_dk<8, kMode, false, kPush>(pl, stream, p, xmap) : launch_dk<16, kMode, false, kPush>(pl, stream, p, xmap);
 }
 
 template <int NB>
@@ -1078,7 +1081,15 @@ static bool dk_eligible(const WeightRef &w, const RowMap &rows, const DispatchTa
 bool dk_gather_ok(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue) {
   static const bool no_gather = [] { const char *e = getenv("FB2_DEBUG_NO_DK_GATHER"); return e && e[0] == '1'; }();
   return !no_gather && w.perm && dk_eligible(w, rows, tbl, epilogue) && w.k % 8 == 0 &&
-         dk::w_stages_for(rows.m * w.k * 2) >= dk::kMinWStages;
+         dk::w_stages_for(false, rows.m * w.k * 2) >= dk::kMinWStages;
+}
+// ... and the routed blocks of an expert stack when they hold at most 8 rows (16 without the SwiGLU epilogue behind
+// FB2_DEBUG_DK_ROUTED_MAXBLOCK=16)
+bool dk_routed_ok(const WeightRef &w, const RowMap &rows, int epilogue) {
+  static const bool no_dk = [] { const char *e = getenv("FB2_DEBUG_NO_DK"); return e && e[0] == '1'; }();
+  static const int max_block = [] { const char *e = getenv("FB2_DEBUG_DK_ROUTED_MAXBLOCK"); return e ? atoi(e) : 8; }();
+  if (no_dk || rows.mode != ROWS_ROUTED) return false;   // (act-order: run_tc permutes x before the launch)
+  return rows.block <= (epilogue ? 8 : (max_block < 16 ? max_block : 16));
 }
 
 bool tc_supported(const WeightRef &w) {
@@ -1133,7 +1144,7 @@ int tc_grid_size(const WeightRef &w, const RowMap &rows, int epilogue, int sm_co
 
 int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, const __half *x,
                    size_t x_rows, __half *y, int epilogue, const TcScratch &scratch, int sm_count,
-                   cudaStream_t stream, const PushTargets *push) {
+                   cudaStream_t stream, const PushTargets *push, int dk_flags, const int32_t *out_map) {
   if (!tc_supported(w)) {
     set_error("tensor-core path needs the tiled weight format (K,N multiples of 128, group 128)");
     return FB2_ERR_UNSUPPORTED;
@@ -1172,7 +1183,7 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
       RowMap sub = rows;
       sub.m = (int)std::min(chunk, (size_t)rows.m - r0);
       int rc = launch_tc_gemm(w, sub, nullptr, x + r0 * w.k, (size_t)sub.m, y + r0 * ld_out, epilogue, scratch, sm_count,
-                              stream, nullptr);
+                              stream, nullptr, 0, nullptr);
       if (rc) return rc;
     }
     return FB2_OK;
@@ -1233,21 +1244,40 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   }
 #endif
   int rc;
-  const bool use_dk = dk_eligible(w, rows, tbl, epilogue) && ((p.x_tma & 1) || w.perm);
-  if (use_dk) {
-    static const bool l2pf = [] { const char *e = getenv("FB2_DEBUG_L2PF"); return e && e[0] == '1'; }();
-    p.l2_prefetch = l2pf ? 1 : 0;
+  const bool use_dk_dense = dk_eligible(w, rows, tbl, epilogue) && ((p.x_tma & 1) || w.perm);
+  const bool use_dk_routed = dk_routed_ok(w, rows, epilogue) && !(push && push->world);
+  if (out_map && !use_dk_routed) {
+    set_error("internal: an output column map needs the routed decode kernel");
+    return FB2_ERR_ARG;
+  }
+  if (use_dk_dense || use_dk_routed) {
+    p.l2_prefetch = 0;
+    p.dk_flags = use_dk_routed ? dk_flags : 0;
+    p.out_map = use_dk_routed ? out_map : nullptr;
     p.fd_grid = make_fastdiv((u32)pl.grid);
-    p.fd_upt = make_fastdiv((u32)p.groups);
+    p.fd_upt = make_fastdiv((u32)(pl.nacc * p.groups));
     p.fd_tiles = make_fastdiv((u32)pl.n_tiles);
     p.fd_units = make_fastdiv((u32)pl.units);
     const bool pushing = push && push->world;
-    if (w.perm) {
-      p.w_stages = dk::w_stages_for(rows.m * w.k * 2);
-      rc = pushing ? launch_dk_rows<true, true>(rows.m, pl, stream, p, xmap) : launch_dk_rows<false, true>(rows.m, pl, stream, p, xmap);
+    if (use_dk_routed) {
+      p.w_stages = dk::w_stages_for(epilogue != 0, 0);
+      if (rows.block <= 8) {
+        rc = epilogue ? launch_dk<8, dk::DK_ROUTED, true, false>(pl, stream, p, xmap)
+                      : launch_dk<8, dk::DK_ROUTED, false, false>(pl, stream, p, xmap);
+      } else if (epilogue) {
+        set_error("internal: SwiGLU decode kernel is instantiated for blocks of <= 8 rows");
+        return FB2_ERR_ARG;
+      } else {
+        rc = launch_dk<16, dk::DK_ROUTED, false, false>(pl, stream, p, xmap);
+      }
+    } else if (w.perm) {
+      p.w_stages = dk::w_stages_for(false, rows.m * w.k * 2);
+      rc = pushing ? launch_dk_rows<dk::DK_GATHER, true>(rows.m, pl, stream, p, xmap)
+                   : launch_dk_rows<dk::DK_GATHER, false>(rows.m, pl, stream, p, xmap);
     } else {
-      p.w_stages = dk::w_stages_for(0);
-      rc = pushing ? launch_dk_rows<true, false>(rows.m, pl, stream, p, xmap) : launch_dk_rows<false, false>(rows.m, pl, stream, p, xmap);
+      p.w_stages = dk::w_stages_for(false, 0);
+      rc = pushing ? launch_dk_rows<dk::DK_DENSE, true>(rows.m, pl, stream, p, xmap)
+                   : launch_dk_rows<dk::DK_DENSE, false>(rows.m, pl, stream, p, xmap);
     }
   } else if (push && push->world) {
     if (tbl || epilogue || nb > 64) {

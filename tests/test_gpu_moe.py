@@ -225,10 +225,13 @@ def test_moe_ffn_tc(fb2, oracle, cuda, batch, act):
     assert st["rel"] < 1e-2 and st["nmse"] < 1e-4, st
 
 
-def test_moe_ffn_qwen3_layer_shape(fb2, oracle, cuda):
-    """BASELINE.json configs[2] shape at full size: E=128, top-8, hidden 2048, inter 768."""
-    for batch in (1, 32):
-        st = _ffn_case(fb2, oracle, cuda, 2048, 768, 128, 8, batch, 128, 0x9E3, None)
+@pytest.mark.parametrize("act,batches", [(None, (1, 2, 4, 8, 16, 32)), ("mod", (1, 8, 32, 40))])
+def test_moe_ffn_qwen3_layer_shape(fb2, oracle, cuda, act, batches):
+    """BASELINE.json configs[2] shape at full size: E=128, top-8, hidden 2048, inter 768, every decode batch of the
+    bench; with act-order stacks the chained form runs (x gathered by the routing launch, act stored in the down
+    stack's column order), and batch 40 takes the unchained path (separate gather launches, 16-row blocks)."""
+    for batch in batches:
+        st = _ffn_case(fb2, oracle, cuda, 2048, 768, 128, 8, batch, 128, 0x9E3, act)
         assert st["rel"] < 1e-2 and st["nmse"] < 1e-4, (batch, st)
 
 
