@@ -220,6 +220,10 @@ def run_gpu(args):
         comm = par.Comm.from_torch_distributed(local)
         comm.enable_p2p(max(DECODE_MS) * max(n for (k, n) in shapes))
 
+    parity = None
+    if world > 1 and not args.quick:
+        parity = parity_check(fb2, par, rank, world, local, comm)
+
     def step_for(ms, fused=True):
         def fn():
             for m in ms:
@@ -330,20 +334,22 @@ def run_gpu(args):
                "d2h_bytes_per_step": sum(b.d2h_bytes for b in batches),
                "ms_per_step": round(e_ms, 3), "api": "fb2_gptq_linear_forward_host_batch"}
     else:
-        # N > 1: host tensors per rank -> H2D, the sharded step, D2H of the reduced outputs
+        # N > 1: the same experiment as N = 1, per rank: every one of the step's GEMMs gets its input from pinned host
+        # memory and returns its (reduced) output there -- 768 H2D and 768 D2H copies per step inside the timed region
         hx = {m: [torch.randn(m, k).half().pin_memory() for (k, n) in shapes] for m in DECODE_MS}
         hy = {m: [torch.empty(m, n, dtype=torch.float16).pin_memory() for (k, n) in shapes] for m in DECODE_MS}
-        step = step_for(DECODE_MS)
 
         def e2e_step():
             for m in DECODE_MS:
-                for j in range(4):
-                    xs[m][j].copy_(hx[m][j], non_blocking=True)
-            step()
-            for m in DECODE_MS:
-                for j in range(4):
-                    hy[m][j].copy_(ys[m][j], non_blocking=True)
-            torch.cuda.synchronize()
+                for li in range(layers):
+                    for j in range(4):
+                        xs[m][j].copy_(hx[m][j], non_blocking=True)
+                        if row_parallel[j]:
+                            comm.forward_allreduce(lins[li][j], xs[m][j], ys[m][j], m)
+                        else:
+                            lins[li][j].forward(xs[m][j], ys[m][j], m)
+                        hy[m][j].copy_(ys[m][j], non_blocking=True)
+                torch.cuda.synchronize()
         for _ in range(3):
             e2e_step()
         barrier(world)
@@ -353,9 +359,10 @@ def run_gpu(args):
         barrier(world)
         e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, world)
         e2e = {"value": round(step_bytes / (e_ms * 1e-3) / 1e9, 1), "unit": "GB/s",
-               "h2d_bytes_per_step": sum(int(t.nbytes) for m in DECODE_MS for t in hx[m]) * world,
-               "d2h_bytes_per_step": sum(int(t.nbytes) for m in DECODE_MS for t in hy[m]) * world,
-               "ms_per_step": round(e_ms, 3), "api": "fb2_gptq_linear_forward / fb2_gptq_linear_forward_allreduce (per rank)"}
+               "h2d_bytes_per_step": sum(int(t.nbytes) for m in DECODE_MS for t in hx[m]) * layers * world,
+               "d2h_bytes_per_step": sum(int(t.nbytes) for m in DECODE_MS for t in hy[m]) * layers * world,
+               "ms_per_step": round(e_ms, 3),
+               "api": "fb2_gptq_linear_forward / fb2_gptq_linear_forward_allreduce per GEMM, host <-> device copies per GEMM (per rank)"}
 
     # ------------------------------------------- Gemma3-27B TP prefill (BASELINE.json configs[4])
     tp_prefill = None
@@ -378,7 +385,9 @@ def run_gpu(args):
         avg_launch_us = ms_step * 1e3 / n_gemms
         achieved = (step_bytes / n_gemms) / (avg_launch_us * 1e-6) / 1e9
         traffic, traffic_note = None, None
-        tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        tp = os.path.join(ROOT, "profiles", "traffic_r02.json")
+        if not os.path.exists(tp):
+            tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
             traffic = tj.get("dram_bytes_per_launch")
@@ -399,19 +408,79 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": pk["src"],
-                         "kernel": "tc_gemm_kernel (stream-K, tcgen05)", "avg_launch_us": round(avg_launch_us, 3),
+                         "kernel": "dk_gemm_kernel (M <= 16) / tc_gemm_kernel (M = 32): stream-K, tcgen05",
+                         "avg_launch_us": round(avg_launch_us, 3),
                          "alg_bytes_per_launch": int(step_bytes / n_gemms)},
             "cpu_baseline": cpu, "series_decode": series, "per_shape_M1": per_shape, "prefill": prefill,
-            "moe_decode": moe, "tp_prefill_gemma3": tp_prefill, "tp_allreduce": tp_allreduce,
+            "moe_decode": moe, "tp_prefill_gemma3": tp_prefill, "tp_allreduce": tp_allreduce, "parity": parity,
             "build_s": round(build_s, 1),
             "host_cores": os.cpu_count(),
         }
         print(json.dumps(line), flush=True)
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write(f"bench: multi-GPU parity check failed: {parity}\n")
+        sys.stderr.flush()
+        os._exit(3)
     if world > 1:
         # leave without the NCCL / CUDA-graph teardown (it can block when graphs hold collectives)
         barrier(world)
         sys.stdout.flush()
         os._exit(0)
+
+
+def parity_check(fb2, par, rank, world, local, comm):
+    """N > 1: the sharded paths against the single-GPU result of the same library on the same inputs (every rank
+    holds the full weights for this one layer): (tp) Llama down_proj, row-parallel, act-order, GEMM + NCCL all-reduce;
+    (tp_fused) the same through the fused push all-reduce of the decode step; (ep) one Qwen3-30B-A3B MoE layer,
+    expert-parallel through fb2_moe_ep_ffn_forward.  Returns max-abs / max-ref per path."""
+    import torch
+    import torch.distributed as dist
+    dev = f"cuda:{local}"
+    rng = np.random.default_rng(4321)                     # same on every rank
+    name, k, n = LLAMA["linears"][3]
+    qw, sc, qz, gi = synth_gptq(rng, k, n, act_order=True)
+    full = fb2.GptqLinear.from_raw(qw, sc, qz, gi, None, 4, GROUP, k, n, device=local)
+    tpl = par.TensorParallelLinear(name, qw, sc, qz, gi, None, 4, GROUP, k, n, rank, world, device=local)
+    out = {}
+    cols = torch.from_numpy(np.asarray(tpl.x_cols, dtype=np.int64)).to(dev)
+    for m, key in ((4, "tp_m4"), (32, "tp_m32")):
+        x = torch.from_numpy(rng.uniform(-1, 1, size=(m, k)).astype(np.float16)).to(dev)
+        y_full = full.forward(x).float()
+        x_loc = x[:, cols].contiguous()
+        y_nccl = tpl.forward(x_loc).float()                                    # GEMM + all-reduce (torch.distributed)
+        y_fused = torch.empty((m, n), dtype=torch.float16, device=dev)
+        comm.forward_allreduce(tpl.linear, x_loc, y_fused, m)                  # fused push all-reduce (decode sizes)
+        torch.cuda.synchronize()
+        ref = y_full.abs().max().item()
+        out[key] = round((y_nccl - y_full).abs().max().item() / ref, 6)
+        out[key.replace("tp_", "tp_fused_")] = round((y_fused.float() - y_full).abs().max().item() / ref, 6)
+    del full, tpl
+    H, I, E, K = QWEN3["hidden"], QWEN3["inter"], QWEN3["experts"], QWEN3["top_k"]
+    gu = [synth_gptq(rng, H, 2 * I, False)[:3] for _ in range(E)]
+    dn = [synth_gptq(rng, I, H, False)[:3] for _ in range(E)]
+    mk = lambda parts, kk, nn: fb2.GptqExpertStack.load_gptq_stacked([q[0] for q in parts], [q[1] for q in parts],
+                                                                    [q[2] for q in parts], None, 4, GROUP, kk, nn, device=local)
+    B = 32
+    ffn = fb2.moe.MoeFfn(mk(gu, H, 2 * I), mk(dn, I, H), K, True, max_batch=B)
+    e_lo, e_hi = rank * E // world, (rank + 1) * E // world
+    ep = par.ExpertParallelFfn(mk(gu[e_lo:e_hi], H, 2 * I), mk(dn[e_lo:e_hi], I, H), K, True, B // world, E, rank, world,
+                               comm=comm).enable_native()
+    fb2.pregrow_scratch(local, B * K)
+    xg = torch.from_numpy(rng.uniform(-1, 1, size=(B, H)).astype(np.float16)).to(dev)
+    lg = torch.from_numpy(rng.uniform(-2, 2, size=(B, E)).astype(np.float16)).to(dev)
+    y_ref = ffn.forward(xg, lg).float()
+    b_loc = B // world
+    sl = slice(rank * b_loc, (rank + 1) * b_loc)
+    y_ep = ep.forward(xg[sl].contiguous(), lg[sl].contiguous()).float()
+    torch.cuda.synchronize()
+    out["ep_b32"] = round((y_ep - y_ref[sl]).abs().max().item() / max(y_ref.abs().max().item(), 1e-6), 6)
+    # worst value over the ranks
+    t = torch.tensor([out[k_] for k_ in sorted(out)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {k_: float(v) for k_, v in zip(sorted(out), t.tolist())}
+    out["tolerance"] = 2e-3
+    out["ok"] = all(v <= 2e-3 for k_, v in out.items() if k_ not in ("tolerance",))
+    return out
 
 
 def run_tp_prefill(args, fb2, par, rank, world, local, pk, comm=None):
@@ -548,7 +617,7 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle
-    threads = oracle.max_threads()
+    all_threads = oracle.max_threads()
     rng = np.random.default_rng(99)
     layer0 = []
     for (name, k, n) in LLAMA["linears"]:
@@ -557,28 +626,37 @@ def run_reference(args):
     ws = [(k, n, oracle.dequant_gptq(qw, sc, qz, gi, 4, GROUP, k, n)) for (_, k, n, qw, sc, qz, gi) in layer0]
     xrng = np.random.default_rng(7)
     xs = {m: [xrng.uniform(-1, 1, size=(m, k)).astype(np.float16).astype(np.float32) for (k, n, _) in ws] for m in DECODE_MS}
-
-    def step():
-        for m in DECODE_MS:
-            for j, (k, n, w) in enumerate(ws):
-                oracle.linear_forward(xs[m][j], w, None, m, threads=threads)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
     b = sum(alg_bytes(k, n, m, not args.no_act_order) for m in DECODE_MS for (k, n, _) in ws)
+
+    def timed(threads, steps, warmup):
+        def step():
+            for m in DECODE_MS:
+                for j, (k, n, w) in enumerate(ws):
+                    oracle.linear_forward(xs[m][j], w, None, m, threads=threads)
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        return (time.perf_counter() - t0) / steps
+    # The reference's Linux CPU GEMM is single-threaded (cpu.rs:481-492): ONE core is the baseline.  A step costs
+    # ~8 s on one core, so the step count is bounded to keep the run within a few minutes.
+    steps1 = max(1, min(args.steps, 4))
+    dt = timed(1, steps1, min(args.warmup, 1))
     v = round(b / dt / 1e9, 4)
+    dt_all = timed(all_threads, 2, 1)
     sample = (f"each step = layer 0's 4 linears at M={DECODE_MS} (24 of the 768 GEMMs of a full step; the other "
-              "31 layers repeat the same shapes), oracle port of the reference CPU path, f64 accumulate")
+              f"31 layers repeat the same shapes), oracle port of the reference CPU path, f64 accumulate; {steps1} timed steps")
     print(json.dumps({
         "impl": "reference", "metric": "w4a16_gemm_decode_throughput", "value": v, "unit": "GB/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3),
+        "n_gpus": args.gpus, "steps": steps1, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 accumulate)",
         "data": "synthetic",
         "config": {"workload": "Llama-3.1-8B GPTQ-Int4 dense linears (qkv/o/gate_up/down), decode M=1..32", "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count(),
+                         "all_cores": {"value": round(b / dt_all / 1e9, 4), "unit": "GB/s", "cores": all_threads,
+                                       "note": "courtesy figure: the reference itself never threads this GEMM"}},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 

@@ -58,6 +58,10 @@ struct DeviceScratch {
   __half *xperm = nullptr;         // act-order: activations with columns gathered into sorted-k order
   size_t xperm_bytes = 0;
   uint32_t *ll = nullptr;          // flag-in-value partial slots (fixed size, all-ones = empty)
+  // Outgrown buffers are RETIRED, never freed: a captured CUDA graph (or a thread that has already read the pool)
+  // may still hold their addresses in kernel parameters.  The pool only grows to the high-water mark of the
+  // process, so what is kept is bounded by the sum of a geometric-ish series of earlier sizes.
+  std::vector<void *> retired;
 };
 static DeviceScratch g_scratch[kMaxDevices];
 
@@ -109,14 +113,15 @@ static int grow_scratch(int device, size_t partial_bytes, size_t counters) {
   s.want_partial_bytes = std::max(s.want_partial_bytes, partial_bytes);
   s.want_counters = std::max(s.want_counters, counters);
   if (s.want_partial_bytes > s.partial_bytes) {
-    if (s.partials) FB2_CUDA_TRY(cudaFree(s.partials));   // implicit device sync
+    if (s.partials) s.retired.push_back(s.partials);
     s.partials = nullptr;
     s.partial_bytes = 0;
     FB2_CUDA_TRY(cudaMalloc(&s.partials, s.want_partial_bytes));
+    FB2_CUDA_TRY(cudaMemset(s.partials, 0, s.want_partial_bytes));
     s.partial_bytes = s.want_partial_bytes;
   }
   if (s.want_counters > s.num_counters) {
-    if (s.counters) FB2_CUDA_TRY(cudaFree(s.counters));
+    if (s.counters) s.retired.push_back(s.counters);
     s.counters = nullptr;
     s.num_counters = 0;
     FB2_CUDA_TRY(cudaMalloc(&s.counters, s.want_counters * sizeof(int32_t)));
@@ -130,7 +135,7 @@ static int grow_xperm(int device, size_t bytes) {
   DeviceScratch &s = g_scratch[device];
   std::lock_guard<std::mutex> lock(s.mu);
   if (bytes <= s.xperm_bytes) return FB2_OK;
-  if (s.xperm) FB2_CUDA_TRY(cudaFree(s.xperm));
+  if (s.xperm) s.retired.push_back(s.xperm);
   s.xperm = nullptr;
   s.xperm_bytes = 0;
   FB2_CUDA_TRY(cudaMalloc((void **)&s.xperm, bytes));
@@ -386,6 +391,12 @@ static int reserve_scratch_for(const WeightRef &w, int device, size_t rows) {
 static int run_tc(const WeightRef &w_in, const RowMap &rm, const DispatchTable *tbl, const __half *x,
                   size_t x_rows, __half *y, int epilogue, int device, cudaStream_t stream,
                   const PushTargets *push = nullptr, int dk_flags = 0, const int32_t *out_map = nullptr) {
+  if (((uintptr_t)x % 16) != 0 || ((uintptr_t)y % 2) != 0) {
+    // every activation path of the tensor-core kernels moves 16-byte vectors (TMA boxes, cp.async rows, the act-order
+    // gathers): a misaligned sub-tensor view is refused here instead of faulting on the device
+    set_error("activations must be 16-byte aligned (x = %p) and the output 2-byte aligned (y = %p)", (const void *)x, (void *)y);
+    return FB2_ERR_ARG;
+  }
   int sms = 0;
   TcScratch sc = current_scratch(device, &sms);
   size_t pb = 0, nc = 0;
@@ -619,11 +630,16 @@ int fb2_gptq_linear_forward(const fb2_linear_t *lin, fb2_stream_t stream, const 
   return launch_generic_gemm(w, rm, (const __half *)x, (__half *)y, 0, st);
 }
 
+static std::mutex &host_call_mutex(int device);   // per device, shared with the batch call (below)
+
 int fb2_gptq_linear_forward_host(fb2_linear_t *lin, const fb2_half *x_host, fb2_half *y_host,
                                  size_t m) {
   if (!lin) { set_error("linear handle is NULL"); return FB2_ERR_ARG; }
   if (m == 0) return FB2_OK;
   if (!x_host || !y_host) { set_error("x / y must not be NULL"); return FB2_ERR_ARG; }
+  // All host-buffer calls of one device share its split-K scratch (indexed by CTA and tile, not by launch): they are
+  // serialised by the per-device mutex that fb2_gptq_linear_forward_host_batch takes as well.
+  std::lock_guard<std::mutex> dev_lock(host_call_mutex(lin->device));
   std::lock_guard<std::mutex> lock(lin->host_mu);
   FB2_CUDA_TRY(cudaSetDevice(lin->device));
   const size_t k = lin->w.k, n = lin->w.n;
@@ -664,6 +680,7 @@ struct HostArena {
   std::vector<cudaEvent_t> ev_in, ev_done;
 };
 static HostArena g_arena[kMaxDevices];
+static std::mutex &host_call_mutex(int device) { return g_arena[device < 0 || device >= kMaxDevices ? 0 : device].mu; }
 
 int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
                                        const fb2_half *const *x_host, fb2_half *const *y_host,

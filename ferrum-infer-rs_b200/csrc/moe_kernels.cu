@@ -200,11 +200,14 @@ align_block_size_kernel(const int32_t *__restrict__ expert_ids,
   // padding slots of this expert's run -> sentinel
   for (int i = total_eq + threadIdx.x; i < padded_e; i += kSortThreads)
     if (pad_off + i < sorted_max) sorted_ids[pad_off + i] = pairs;
+  // everything is clamped to the caller's capacity: an undersized sorted_max truncates the plan (the GEMM then
+  // sees only whole blocks below it) instead of writing past block_ids / walking past sorted_ids
+  const int max_blocks = sorted_max / block_size;
   for (int b = threadIdx.x; b < padded_e / block_size; b += kSortThreads)
-    block_ids[pad_off / block_size + b] = e;
+    if (pad_off / block_size + b < max_blocks) block_ids[pad_off / block_size + b] = e;
   if (e == num_experts - 1) {
     for (int i = total_pad + threadIdx.x; i < sorted_max; i += kSortThreads) sorted_ids[i] = pairs;
-    if (threadIdx.x == 0) total_post_pad[0] = total_pad;
+    if (threadIdx.x == 0) total_post_pad[0] = min(total_pad, max_blocks * block_size);
   }
 }
 
@@ -324,13 +327,14 @@ route_align_small_kernel(const __half *__restrict__ logits, int32_t *__restrict_
       if (e < num_experts) s_off[e] = carry + incl - padded;
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) { s_off[num_experts] = carry; total_post_pad[0] = carry; }
+    if (lane == 0) { s_off[num_experts] = carry; total_post_pad[0] = min(carry, (sorted_max / block_size) * block_size); }
   }
   __syncthreads();
   const int total = min(s_off[num_experts], sorted_max);
   for (int i = threadIdx.x; i < total; i += kRouteAlignThreads) sorted_ids[i] = pairs;   // sentinel
   for (int e = threadIdx.x; e < num_experts; e += kRouteAlignThreads)
-    for (int b = s_off[e] / block_size; b < s_off[e + 1] / block_size; b++) block_ids[b] = e;
+    for (int b = s_off[e] / block_size; b < s_off[e + 1] / block_size; b++)
+      if (b < sorted_max / block_size) block_ids[b] = e;
   __syncthreads();
   for (int pidx = threadIdx.x; pidx < pairs; pidx += kRouteAlignThreads) {
     const int row = pidx / top_k;

@@ -37,6 +37,10 @@ namespace dk {
 enum { DK_DENSE = 0, DK_GATHER = 1, DK_ROUTED = 2 };
 
 constexpr int kNB = 16;                     // UMMA N: rows of a block (<= 16 real)
+constexpr int kWarpMma2 = 11;               // second MMA issuer: one per dequant group, so the groups are not coupled through
+                                            // one in-order issue loop (the 12th warp costs no registers: 11 warps already
+                                            // occupy the allocation of 12)
+constexpr int kDkThreads = 12 * 32;
 constexpr int kXSlots = 4;
 constexpr int kXBytes = kNB * 256;          // [2 atoms][16 rows][128 B]
 constexpr int kSmemBudget = 108 * 1024;     // two CTAs per SM
@@ -212,7 +216,7 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       ptx::mbar_fence_init();
     }
     __syncwarp();
-    ptx::named_bar_arrive(2, kThreads);
+    ptx::named_bar_arrive(2, kDkThreads);
   } else if (warp == kWarpMma) {
     if (lane == 0) {
       for (int i = 0; i < 2; i++) {
@@ -225,9 +229,9 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
     ptx::tmem_alloc<kTmemCols>(ptx::smem_u32(s_tmem));
   }
   uint32_t tmem_base = 0;
-  if (warp != kWarpW && warp != kWarpX) {
+  if (warp != kWarpW && warp != kWarpX) {      // (the second MMA warp takes part like a dequant warp)
     ptx::tc_fence_before();
-    ptx::named_bar_sync(2, kThreads);
+    ptx::named_bar_sync(2, kDkThreads);
     ptx::tc_fence_after();
     tmem_base = *s_tmem;
   }
@@ -267,11 +271,11 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
             ptx::bulk_g2s_hint(smem_base + L::kWBase + wp.st * kStageBytes, wsrc, kStageBytes, full, pol);
           }
           __syncwarp();
-          if (it == 0) ptx::named_bar_arrive(2, kThreads);       // ring barriers are initialised (setup barrier)
+          if (it == 0) ptx::named_bar_arrive(2, kDkThreads);       // ring barriers are initialised (setup barrier)
         }
       }
     }
-    if (it == 0) ptx::named_bar_arrive(2, kThreads);             // routed launch with nothing for this CTA
+    if (it == 0) ptx::named_bar_arrive(2, kDkThreads);             // routed launch with nothing for this CTA
   } else if (warp == kWarpX) {
     // ====================================================== activation producer (L2 hits)
     if (kMode == DK_DENSE && lane == 0) ptx::prefetch_tensormap(xmap);
@@ -377,27 +381,28 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
         }
       }
     }
-  } else if (warp == kWarpMma) {
-    // ==================================================================== MMA issuer
+  } else if (warp == kWarpMma || warp == kWarpMma2) {
+    // ==================================================================== MMA issuers (one per group / A slot)
     plan_routed();
     const u32 n_units = pl.u1 - pl.u0;
     constexpr uint32_t idesc = ptx::umma_idesc_f16(128, kNB);
     const uint64_t b_desc_ring = ptx::umma_desc_kmajor_sw128(smem_base);
-    RingPos xp{0, 0};
+    const uint32_t s = warp == kWarpMma2 ? 1u : 0u;
+    const uint32_t a = tmem_base + kColA + s * 64;
+    const uint32_t d = tmem_base + kColD + s * kNB, zc = tmem_base + kColZ + s * 8;
+    static_assert(SX == 4, "activation ring position is computed from the unit index");
 #pragma unroll 1
-    for (u32 li = 0; li < n_units; li++, xp.advance(SX)) {
-      const uint32_t s = li & 1u;
-      ptx::mbar_wait(bar(BAR_FULL_X + xp.st), xp.par);            // activation slice landed
+    for (u32 li = s; li < n_units; li += 2) {
+      const uint32_t xst = li & 3u, xpar = (li >> 2) & 1u;
+      ptx::mbar_wait(bar(BAR_FULL_X + xst), xpar);                // activation slice landed
       if (kRouted) ptx::fence_proxy_async_smem();                 // cp.async rows were generic-proxy writes
       if (li == 0) FB2_TLW(13);
       ptx::mbar_wait(bar(BAR_FULL_A + s), (li >> 1) & 1u);        // raw nibbles of the unit are in A slot s
       if (li == 0) FB2_TLW(14);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        const uint64_t b0 = b_desc_ring + (uint64_t)((xp.st * kXBytes) >> 4);
+        const uint64_t b0 = b_desc_ring + (uint64_t)((xst * kXBytes) >> 4);
         const uint64_t b1 = b0 + (uint64_t)((kNB * 128) >> 4);    // second 64-k atom
-        const uint32_t a = tmem_base + kColA + s * 64;
-        const uint32_t d = tmem_base + kColD + s * kNB, zc = tmem_base + kColZ + s * 8;
         // hi class (q * 2^-20): k-steps 2, 3 of each 64-k half; the first MMA of a unit overwrites D
         ptx::umma_f16_ts(d, a + 16, b0 + 4, idesc, 0u);
         ptx::umma_f16_ts(d, a + 24, b0 + 6, idesc, 1u);
@@ -414,7 +419,7 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) ptx::umma_f16_ts(d, zc, b1 + (uint64_t)(kk * 2), idesc, 1u);
         ptx::tc_commit(bar(BAR_DONE + s));                         // A slot s free, D[s] complete
-        ptx::tc_commit(bar(BAR_EMPTY_X + xp.st));                  // activation slot consumed
+        ptx::tc_commit(bar(BAR_EMPTY_X + xst));                    // activation slot consumed
       }
       __syncwarp();
     }
@@ -870,7 +875,7 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
 }
 
 template <int R, int kMode, bool kSilu, bool kPush>
-__global__ void __launch_bounds__(384, 2) dk_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
+__global__ void __launch_bounds__(kDkThreads, 2) dk_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
   if (!(p.dk_flags & DKF_LATE_TRIGGER)) ptx::launch_dependents();
   dk_body<R, kMode, kSilu, kPush>(p, &xmap);
 }

@@ -1046,6 +1046,7 @@ int launch_dk(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CU
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   launch_cfg(cfg, attr, pl, stream);
+  cfg.blockDim = dim3(dk::kDkThreads);
   cfg.dynamicSmemBytes = dk::kSmemBudget;
   FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, dk::dk_gemm_kernel<R, kMode, kSilu, kPush>, p, xmap));
   return FB2_OK;
@@ -1071,10 +1072,10 @@ int launch_dispatch(const TcPlan &pl, cudaStream_t stream, const TcParams &p, co
 
 }  // namespace
 
-// The decode kernel (tc_decode.cuh) serves dense launches of at most 8 rows.
+// The decode kernel (tc_decode.cuh) serves dense launches of at most 16 rows.
 static bool dk_eligible(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue) {
   static const bool no_dk = [] { const char *e = getenv("FB2_DEBUG_NO_DK"); return e && e[0] == '1'; }();
-  static const int max_m = [] { const char *e = getenv("FB2_DEBUG_DK_MAXM"); return e ? atoi(e) : 8; }();
+  static const int max_m = [] { const char *e = getenv("FB2_DEBUG_DK_MAXM"); return e ? atoi(e) : 16; }();
   return !no_dk && rows.mode == ROWS_DENSE && rows.m >= 1 && rows.m <= max_m && rows.m <= 16 && !epilogue && !tbl;
 }
 // ... and gathers act-order activations itself when the m rows of x fit next to a weight ring of kMinWStages

@@ -109,8 +109,8 @@ def test_anchor_4096(fb2, oracle, cuda):
 
 @pytest.mark.parametrize("k,n", [(5376, 4096), (5376, 2048), (4096, 5376)])
 def test_gemma3_shapes_desc_act(fb2, oracle, cuda, k, n):
-    """gptq_parity_test.rs:592-660 (Gemma3-27B shapes, desc_act): the two 21504-wide shapes
-    are covered at full size by the property tests below."""
+    """gptq_parity_test.rs:592-660 (Gemma3-27B shapes, desc_act).  The two 21504 / 43008-wide shapes of the
+    same fixture are checked at full size by test_gemma3_wide_shapes_full_size (sampled columns)."""
     syn, gi = _make(oracle, k, n, 128, 0x6E33A + k + n, "mod")
     lin = fb2.GptqLinear.from_raw(syn.qweight, syn.scales, syn.qzeros, gi, None, 4, 128, k, n)
     _check_forward(oracle, cuda, lin, syn, gi, 2)
@@ -180,6 +180,44 @@ def test_full_size_linearity_and_column_probe(fb2, oracle, cuda):
     ref = oracle.gemm(x, np.ascontiguousarray(w_ref[pick]), 8, len(pick), k, threads=8)
     st = oracle.error_stats(y8.float().cpu().numpy()[:, pick], ref)
     assert st["rel"] < REL_TOL and st["nmse"] < NMSE_TOL, st
+
+
+def _sampled_forward_check(fb2, oracle, cuda, k, n, seed, act, ms, col_stride, row_cap=48):
+    """Full-size linear against the oracle on a SAMPLE of the output: every col_stride-th block of 8 columns (the
+    oracle dequantises only those columns: the packed tensors are sliced on 8-column boundaries, where the zero-point
+    words split cleanly) and at most row_cap rows spread over the batch.  The GPU computes everything."""
+    syn, gi = _make(oracle, k, n, 128, seed, act)
+    lin = fb2.GptqLinear.from_raw(syn.qweight, syn.scales, syn.qzeros, gi, None, 4, 128, k, n)
+    blocks = np.arange(0, n // 8, col_stride)
+    cols = (blocks[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+    w_ref = oracle.dequant_gptq(np.ascontiguousarray(syn.qweight[:, cols]), np.ascontiguousarray(syn.scales[:, cols]),
+                                np.ascontiguousarray(syn.qzeros[:, blocks]), gi, 4, 128, k, len(cols))
+    out = {}
+    for m in ms:
+        x = _x(oracle, m, k, seed=0xC0FFEE + m)
+        y = lin.forward(cuda.from_numpy(x.astype(np.float16)).cuda())
+        cuda.cuda.synchronize()
+        rows = np.unique(np.linspace(0, m - 1, min(m, row_cap)).astype(int))
+        ref = oracle.gemm(np.ascontiguousarray(x[rows]), w_ref, len(rows), len(cols), k, threads=8)
+        st = oracle.error_stats(y.float().cpu().numpy()[np.ix_(rows, cols)], ref)
+        assert st["rel"] < REL_TOL and st["nmse"] < NMSE_TOL, (lin.kernel_name(m), k, n, m, st)
+        out[m] = st
+    return out
+
+
+@pytest.mark.parametrize("name,k,n", [("qkv_proj", 4096, 6144), ("o_proj", 4096, 4096), ("gate_up_proj", 4096, 28672),
+                                      ("down_proj", 14336, 4096)])
+def test_llama_shapes_full_size(fb2, oracle, cuda, name, k, n):
+    """BASELINE.json configs[1] at full size, act-order: every decode kernel class (M = 1: in-kernel gather; 8, 16:
+    gather launch + decode kernel; 32: the 64-row-block kernel) and the prefill class the bench times (M = 512)."""
+    _sampled_forward_check(fb2, oracle, cuda, k, n, 0x77A0 + n, "rand", (1, 2, 8, 16, 32, 512), col_stride=max(1, n // 8 // 24))
+
+
+@pytest.mark.parametrize("name,k,n,ms", [("gate_up_proj", 5376, 43008, (2, 4096)), ("down_proj", 21504, 5376, (2, 4096))])
+def test_gemma3_wide_shapes_full_size(fb2, oracle, cuda, name, k, n, ms):
+    """gptq_parity_test.rs:592-660: the Gemma3-27B shapes with N = 43008 and K = 21504 (desc_act), at the reference
+    test's M = 2 and at the prefill batch the tensor-parallel bench runs (M = 4096: 256-row blocks)."""
+    _sampled_forward_check(fb2, oracle, cuda, k, n, 0x6E33A + k + n, "mod", ms, col_stride=max(1, n // 8 // 16), row_cap=24)
 
 
 def test_graph_capture_and_replay(fb2, oracle, cuda):
