@@ -11,7 +11,8 @@ repo's name, which is not a Python identifier).
 """
 from ._ffi import Fb2Error, lib, launch_count, reset_launch_count, LIB_PATH  # noqa: F401
 from .gptq import (QuantConfig, GptqLinear, StackedExpertLinear, GptqExpertStack,  # noqa: F401
-                   gemm_algorithmic_bytes, gemm_flops, pregrow_scratch, forward_host_batch, HostBatch)
+                   gemm_algorithmic_bytes, gemm_flops, pregrow_scratch, forward_host_batch, HostBatch,
+                   fused_add_rms_norm, argmax_rows)
 from . import moe  # noqa: F401
 
 __version__ = "0.1.0"

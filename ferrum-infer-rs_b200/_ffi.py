@@ -84,6 +84,11 @@ SIGNATURES = {
     "fb2_moe_weighted_sum_batched": (_i32, [_vp, _vp, _vp, _vp, _sz, _sz, _sz]),
     "fb2_fused_silu_mul_split": (_i32, [_vp, _vp, _vp, _sz, _sz]),
     "fb2_fused_gelu_tanh_mul_split": (_i32, [_vp, _vp, _vp, _sz, _sz]),
+    "fb2_fused_add_rms_norm": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, C.c_float, _vp]),
+    "fb2_gptq_linear_act_order_perm": (_i32, [_vp, C.POINTER(_vp)]),
+    "fb2_gptq_linear_forward_sorted": (_i32, [_vp, _vp, _vp, _vp, _sz]),
+    "fb2_gptq_linear_forward_swiglu": (_i32, [_vp, _vp, _vp, _vp, _sz, _i32]),
+    "fb2_argmax_rows_f16": (_i32, [_vp, _vp, _sz, _sz, _vp]),
     "fb2_moe_ffn_workspace_bytes": (_sz, [_vp, _vp, _sz, _sz]),
     "fb2_moe_ffn_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _i32, _vp, _sz]),
     "fb2_gptq_shard_dims": (_i32, [_sz, _sz, _sz, _i32, _i32, _i32, _vp, _i32, C.POINTER(_sz), C.POINTER(_sz)]),

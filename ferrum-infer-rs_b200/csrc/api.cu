@@ -632,6 +632,58 @@ int fb2_gptq_linear_forward(const fb2_linear_t *lin, fb2_stream_t stream, const 
 
 static std::mutex &host_call_mutex(int device);   // per device, shared with the batch call (below)
 
+// x already in this layer's act-order column order (x_sorted[:, j] = x[:, perm[j]]): the producer folded the gather
+// into its own store (fb2_fused_add_rms_norm with out_perm = fb2_gptq_linear_act_order_perm).
+int fb2_gptq_linear_forward_sorted(const fb2_linear_t *lin, fb2_stream_t stream, const fb2_half *x_sorted,
+                                   fb2_half *y, size_t m) {
+  if (!lin) { set_error("linear handle is NULL"); return FB2_ERR_ARG; }
+  if (m == 0) return FB2_OK;
+  if (!x_sorted || !y) { set_error("x / y must not be NULL"); return FB2_ERR_ARG; }
+  if (m > (size_t)INT32_MAX / 2) { set_error("m too large"); return FB2_ERR_SHAPE; }
+  FB2_CUDA_TRY(cudaSetDevice(lin->device));
+  WeightRef w = view_of(lin);
+  if (!tc_supported(w)) {
+    if (w.g_idx) { set_error("forward_sorted: this act-order layer is served by the generic kernel, which reads x in disk order"); return FB2_ERR_UNSUPPORTED; }
+    RowMap rmg{}; rmg.mode = ROWS_DENSE; rmg.m = (int)m;
+    return launch_generic_gemm(w, rmg, (const __half *)x_sorted, (__half *)y, 0, (cudaStream_t)stream);
+  }
+  w.perm = nullptr;
+  RowMap rm{};
+  rm.mode = ROWS_DENSE;
+  rm.m = (int)m;
+  return run_tc(w, rm, nullptr, (const __half *)x_sorted, m, (__half *)y, 0, lin->device, (cudaStream_t)stream);
+}
+
+int fb2_gptq_linear_act_order_perm(const fb2_linear_t *lin, const int32_t **perm_dev) {
+  if (!lin || !perm_dev) { set_error("NULL argument"); return FB2_ERR_ARG; }
+  *perm_dev = tc_supported(lin->w) ? lin->w.perm : nullptr;
+  return FB2_OK;
+}
+
+// gate | up linear (n = 2 * inter, gate columns first) with SiLU(gate) * up in the GEMM epilogue: y [m, n / 2].
+// (reference: the pair Linear::forward + fused_silu_mul_split, llama_family.rs:3468-3509)
+int fb2_gptq_linear_forward_swiglu(const fb2_linear_t *lin, fb2_stream_t stream, const fb2_half *x, fb2_half *y,
+                                   size_t m, int x_is_sorted) {
+  if (!lin) { set_error("linear handle is NULL"); return FB2_ERR_ARG; }
+  if (m == 0) return FB2_OK;
+  if (!x || !y) { set_error("x / y must not be NULL"); return FB2_ERR_ARG; }
+  if (m > (size_t)INT32_MAX / 2) { set_error("m too large"); return FB2_ERR_SHAPE; }
+  FB2_CUDA_TRY(cudaSetDevice(lin->device));
+  WeightRef w = view_of(lin);
+  if (w.n % 2) { set_error("SwiGLU needs an even number of output features"); return FB2_ERR_SHAPE; }
+  if (w.bias) { set_error("SwiGLU epilogue: a gate|up layer with bias is not supported"); return FB2_ERR_UNSUPPORTED; }
+  RowMap rm{};
+  rm.mode = ROWS_DENSE;
+  rm.m = (int)m;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tc_supported(w) && (w.n / 2) % kTileN == 0) {
+    if (x_is_sorted) w.perm = nullptr;
+    return run_tc(w, rm, nullptr, (const __half *)x, m, (__half *)y, 1, lin->device, st);
+  }
+  if (x_is_sorted && w.g_idx) { set_error("forward_swiglu: sorted input needs the tiled weight format"); return FB2_ERR_UNSUPPORTED; }
+  return launch_generic_gemm(w, rm, (const __half *)x, (__half *)y, 1, st);
+}
+
 int fb2_gptq_linear_forward_host(fb2_linear_t *lin, const fb2_half *x_host, fb2_half *y_host,
                                  size_t m) {
   if (!lin) { set_error("linear handle is NULL"); return FB2_ERR_ARG; }
@@ -1175,6 +1227,22 @@ int fb2_fused_gelu_tanh_mul_split(fb2_stream_t stream, const fb2_half *gate_up, 
   if (tokens * im == 0) return FB2_OK;
   if (!gate_up || !out) { set_error("NULL argument"); return FB2_ERR_ARG; }
   return launch_silu_mul_split((const __half *)gate_up, (__half *)out, tokens, im, 1, (cudaStream_t)stream);
+}
+
+int fb2_fused_add_rms_norm(fb2_stream_t stream, const fb2_half *input, fb2_half *residual, const fb2_half *weight,
+                           fb2_half *output, size_t tokens, size_t hidden, float eps, const int32_t *out_perm) {
+  if (tokens * hidden == 0) return FB2_OK;
+  if (!input || !weight || !output) { set_error("NULL argument"); return FB2_ERR_ARG; }
+  if (hidden > 64 * 1024) { set_error("hidden %zu too large for the one-CTA-per-token norm", hidden); return FB2_ERR_UNSUPPORTED; }
+  if (input == output && out_perm) { set_error("a permuted output cannot alias the input"); return FB2_ERR_ARG; }
+  return launch_add_rms_norm((const __half *)input, (__half *)residual, (const __half *)weight, (__half *)output, out_perm,
+                             (int)tokens, (int)hidden, eps, (cudaStream_t)stream);
+}
+
+int fb2_argmax_rows_f16(fb2_stream_t stream, const fb2_half *logits, size_t m, size_t n, int32_t *out_idx) {
+  if (m == 0) return FB2_OK;
+  if (!logits || !out_idx || n == 0) { set_error("NULL / empty argument"); return FB2_ERR_ARG; }
+  return launch_argmax_rows((const __half *)logits, (int)m, (int)n, out_idx, (cudaStream_t)stream);
 }
 
 // --------------------------------------------------------------------- fused MoE FFN

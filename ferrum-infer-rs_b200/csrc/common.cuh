@@ -128,6 +128,9 @@ int launch_permute_cols(const __half *x, const int32_t *perm, __half *xp, int m,
                         cudaStream_t stream);
 int launch_silu_mul_split(const __half *gu, __half *out, size_t tokens, size_t im, int gelu,
                           cudaStream_t stream);
+int launch_add_rms_norm(const __half *input, __half *residual, const __half *weight, __half *output,
+                        const int32_t *out_perm, int tokens, int hidden, float eps, cudaStream_t stream);
+int launch_argmax_rows(const __half *logits, int m, int n, int32_t *out, cudaStream_t stream);
 // moe_kernels.cu
 int launch_route_topk_softmax(const __half *logits, int32_t *ids, float *wts, int batch,
                               int num_experts, int top_k, int norm, cudaStream_t stream);

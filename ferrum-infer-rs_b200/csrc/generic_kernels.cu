@@ -264,7 +264,110 @@ __global__ void act_mul_split_kernel(const __half *__restrict__ gu, __half *__re
   out[idx] = __float2half_rn(kGelu ? gelu_tanh_mul(g, u) : silu_mul(g, u));
 }
 
+// Residual add + RMSNorm (reference: kernels/fused_add_rms_norm.cu:21-60, rms_norm.cu), one CTA per token, with the
+// act-order column gather of the linear that consumes the result folded into the store: out[:, j] = normed[:, perm[j]].
+// (The reference runs gather_columns.cu as a separate launch in front of every act-order Marlin call.)
+// f16 in/out, f32 arithmetic; the sum x + r is rounded to f16 (it IS the new residual) before it is normalised, as
+// the reference does.
+__global__ void __launch_bounds__(1024) add_rms_norm_kernel(const __half *__restrict__ input, __half *__restrict__ residual,
+                                                            const __half *__restrict__ weight, __half *__restrict__ output,
+                                                            const int32_t *__restrict__ out_perm, int hidden, float eps) {
+  extern __shared__ __align__(16) __half s_row[];       // the (updated) residual row
+  __shared__ float s_part[32];
+  __shared__ float s_inv;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const size_t off = (size_t)blockIdx.x * hidden;
+  float var = 0.f;
+  for (int i = threadIdx.x; i < hidden; i += blockDim.x) {
+    float v = __half2float(input[off + i]);
+    if (residual) v += __half2float(residual[off + i]);
+    const __half hv = __float2half(v);
+    if (residual) residual[off + i] = hv;
+    s_row[i] = hv;
+    const float r = __half2float(hv);
+    var += r * r;
+  }
+  for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = var;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x + 31) / 32 ? s_part[threadIdx.x] : 0.f;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) s_inv = rsqrtf(v / (float)hidden + eps);
+  }
+  __syncthreads();
+  const float inv = s_inv;
+  for (int j = threadIdx.x; j < hidden; j += blockDim.x) {
+    const int i = out_perm ? out_perm[j] : j;
+    output[off + j] = __float2half(__half2float(s_row[i]) * inv * __half2float(weight[i]));
+  }
+}
+
+// Row argmax of f16 logits (reference: kernels/argmax_rows.cu: one CTA per row, ties -> lowest index).
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const __half *__restrict__ logits, int n, int32_t *__restrict__ out) {
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const __half *row = logits + (size_t)blockIdx.x * n;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = __half2float(row[i]);
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++)
+      if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) { best = s_v[w]; bi = s_i[w]; }
+    out[blockIdx.x] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
 }  // namespace
+
+int launch_add_rms_norm(const __half *input, __half *residual, const __half *weight, __half *output,
+                        const int32_t *out_perm, int tokens, int hidden, float eps, cudaStream_t stream) {
+  if (tokens <= 0) return FB2_OK;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tokens);
+  cfg.blockDim = dim3(hidden >= 1024 ? 1024 : ((hidden + 31) / 32) * 32);
+  cfg.dynamicSmemBytes = (size_t)hidden * sizeof(__half);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cfg.dynamicSmemBytes > 48 * 1024)
+    FB2_CUDA_TRY(cudaFuncSetAttribute(add_rms_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, add_rms_norm_kernel, input, residual, weight, output, out_perm, hidden, eps));
+  count_launch();
+  return FB2_OK;
+}
+
+int launch_argmax_rows(const __half *logits, int m, int n, int32_t *out, cudaStream_t stream) {
+  if (m <= 0) return FB2_OK;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(m);
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, argmax_rows_kernel, logits, n, out));
+  count_launch();
+  return FB2_OK;
+}
 
 int launch_generic_gemm(const WeightRef &w, const RowMap &rows, const __half *x, __half *y,
                         int epilogue, cudaStream_t stream) {

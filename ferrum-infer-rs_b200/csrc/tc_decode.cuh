@@ -154,7 +154,7 @@ template <int R, int kMode, bool kSilu, bool kPush>
 __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "rows per thread");
-  static_assert(!(kSilu && kMode != DK_ROUTED) && !(kPush && kMode == DK_ROUTED), "combination not instantiated");
+  static_assert(!(kSilu && kPush) && !(kPush && kMode == DK_ROUTED), "combination not instantiated");
   using L = Lay<kSilu>;
   constexpr int NACC = L::kNacc;
   constexpr int SX = kXSlots;
@@ -289,7 +289,8 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       ptx::fence_proxy_async_smem();
     }
     if (kGather) {
-      const int g_first = (int)(pl.u0 - fdiv(pl.u0, p.fd_upt) * (u32)upt);
+      int g_first = (int)(pl.u0 - fdiv(pl.u0, p.fd_upt) * (u32)upt);
+      if (NACC == 2 && g_first >= groups) g_first -= groups;      // an up-projection unit reads the same slice as its gate unit
       pm = __ldg(reinterpret_cast<const int4 *>(p.w.perm + (size_t)g_first * kGroup) + lane);   // a weight-side constant
     }
     ptx::grid_dependency_wait();
@@ -360,7 +361,7 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
           const int4 cur = pm;
           {
             // perm of the unit after this one (the next group of the tile, or group 0 of the next tile)
-            const int gn = g + 1 < upt ? g + 1 : 0;
+            const int gn = g + 1 < groups ? g + 1 : 0;
             pm = __ldg(reinterpret_cast<const int4 *>(p.w.perm + (size_t)gn * kGroup) + lane);
           }
           const uint32_t chunk = (uint32_t)(lane >> 1) & 7u, atom = (uint32_t)lane >> 4, sub = (uint32_t)(lane & 1) * 8u;

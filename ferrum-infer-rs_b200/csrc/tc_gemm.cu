@@ -1051,6 +1051,12 @@ int launch_dk(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CU
   FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, dk::dk_gemm_kernel<R, kMode, kSilu, kPush>, p, xmap));
   return FB2_OK;
 }
+template <int kMode>
+int launch_dk_rows_silu(int m, const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
+  return m <= 1 ? launch_dk<1, kMode, true, false>(pl, stream, p, xmap)
+         : m <= 2 ? launch_dk<2, kMode, true, false>(pl, stream, p, xmap)
+         : m <= 4 ? launch_dk<4, kMode, true, false>(pl, stream, p, xmap) : launch_dk<8, kMode, true, false>(pl, stream, p, xmap);
+}
 template <int kMode, bool kPush>
 int launch_dk_rows(int m, const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
   return m <= 1 ? launch_dk<1, kMode, false, kPush>(pl, stream, p, xmap)
@@ -1072,17 +1078,18 @@ int launch_dispatch(const TcPlan &pl, cudaStream_t stream, const TcParams &p, co
 
 }  // namespace
 
-// The decode kernel (tc_decode.cuh) serves dense launches of at most 16 rows.
+// The decode kernel (tc_decode.cuh) serves dense launches of at most 16 rows (8 with the SwiGLU epilogue: two
+// accumulators' worth of running sums per thread).
 static bool dk_eligible(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue) {
   static const bool no_dk = [] { const char *e = getenv("FB2_DEBUG_NO_DK"); return e && e[0] == '1'; }();
   static const int max_m = [] { const char *e = getenv("FB2_DEBUG_DK_MAXM"); return e ? atoi(e) : 16; }();
-  return !no_dk && rows.mode == ROWS_DENSE && rows.m >= 1 && rows.m <= max_m && rows.m <= 16 && !epilogue && !tbl;
+  return !no_dk && rows.mode == ROWS_DENSE && rows.m >= 1 && rows.m <= max_m && rows.m <= (epilogue ? 8 : 16) && !tbl;
 }
 // ... and gathers act-order activations itself when the m rows of x fit next to a weight ring of kMinWStages
 bool dk_gather_ok(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue) {
   static const bool no_gather = [] { const char *e = getenv("FB2_DEBUG_NO_DK_GATHER"); return e && e[0] == '1'; }();
   return !no_gather && w.perm && dk_eligible(w, rows, tbl, epilogue) && w.k % 8 == 0 &&
-         dk::w_stages_for(false, rows.m * w.k * 2) >= dk::kMinWStages;
+         dk::w_stages_for(epilogue != 0, rows.m * w.k * 2) >= dk::kMinWStages;
 }
 // ... and the routed blocks of an expert stack when they hold at most 8 rows (16 without the SwiGLU epilogue behind
 // FB2_DEBUG_DK_ROUTED_MAXBLOCK=16)
@@ -1245,7 +1252,7 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
   }
 #endif
   int rc;
-  const bool use_dk_dense = dk_eligible(w, rows, tbl, epilogue) && ((p.x_tma & 1) || w.perm);
+  const bool use_dk_dense = dk_eligible(w, rows, tbl, epilogue) && ((p.x_tma & 1) || w.perm) && !(epilogue && push && push->world);
   const bool use_dk_routed = dk_routed_ok(w, rows, epilogue) && !(push && push->world);
   if (out_map && !use_dk_routed) {
     set_error("internal: an output column map needs the routed decode kernel");
@@ -1272,13 +1279,15 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
         rc = launch_dk<16, dk::DK_ROUTED, false, false>(pl, stream, p, xmap);
       }
     } else if (w.perm) {
-      p.w_stages = dk::w_stages_for(false, rows.m * w.k * 2);
-      rc = pushing ? launch_dk_rows<dk::DK_GATHER, true>(rows.m, pl, stream, p, xmap)
-                   : launch_dk_rows<dk::DK_GATHER, false>(rows.m, pl, stream, p, xmap);
+      p.w_stages = dk::w_stages_for(epilogue != 0, rows.m * w.k * 2);
+      rc = epilogue ? launch_dk_rows_silu<dk::DK_GATHER>(rows.m, pl, stream, p, xmap)
+           : pushing ? launch_dk_rows<dk::DK_GATHER, true>(rows.m, pl, stream, p, xmap)
+                     : launch_dk_rows<dk::DK_GATHER, false>(rows.m, pl, stream, p, xmap);
     } else {
-      p.w_stages = dk::w_stages_for(false, 0);
-      rc = pushing ? launch_dk_rows<dk::DK_DENSE, true>(rows.m, pl, stream, p, xmap)
-                   : launch_dk_rows<dk::DK_DENSE, false>(rows.m, pl, stream, p, xmap);
+      p.w_stages = dk::w_stages_for(epilogue != 0, 0);
+      rc = epilogue ? launch_dk_rows_silu<dk::DK_DENSE>(rows.m, pl, stream, p, xmap)
+           : pushing ? launch_dk_rows<dk::DK_DENSE, true>(rows.m, pl, stream, p, xmap)
+                     : launch_dk_rows<dk::DK_DENSE, false>(rows.m, pl, stream, p, xmap);
     }
   } else if (push && push->world) {
     if (tbl || epilogue || nb > 64) {

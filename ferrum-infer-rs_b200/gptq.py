@@ -116,6 +116,42 @@ class _LinearBase:
 
     __call__ = forward
 
+    def act_order_perm(self) -> Optional[torch.Tensor]:
+        """The layer's act-order column order as a device int32 tensor view (sorted position -> input column), or None.
+        Feed it to fused_add_rms_norm(out_perm=...) and call forward_sorted / forward_swiglu(x_is_sorted=True)."""
+        p = C.c_void_p()
+        check(lib().fb2_gptq_linear_act_order_perm(self._h, C.byref(p)))
+        return p.value
+
+    def forward_sorted(self, x_sorted: torch.Tensor, out: Optional[torch.Tensor] = None, m: Optional[int] = None) -> torch.Tensor:
+        """fb2_gptq_linear_forward_sorted: x already in this layer's act-order column order."""
+        k, n = self.in_features(), self.out_features()
+        if m is None:
+            m = x_sorted.numel() // k
+        if out is None:
+            out = torch.empty((m, n), dtype=torch.float16, device=x_sorted.device)
+        if m == 0:
+            return out
+        _check_dev_f16(x_sorted, "input", m * k)
+        _check_dev_f16(out, "out", m * n)
+        check(lib().fb2_gptq_linear_forward_sorted(self._h, _stream(), x_sorted.data_ptr(), out.data_ptr(), m))
+        return out
+
+    def forward_swiglu(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, m: Optional[int] = None,
+                       x_is_sorted: bool = False) -> torch.Tensor:
+        """fb2_gptq_linear_forward_swiglu: this gate|up layer with SiLU(gate) * up in the epilogue -> [m, N / 2]."""
+        k, n = self.in_features(), self.out_features()
+        if m is None:
+            m = x.numel() // k
+        if out is None:
+            out = torch.empty((m, n // 2), dtype=torch.float16, device=x.device)
+        if m == 0:
+            return out
+        _check_dev_f16(x, "input", m * k)
+        _check_dev_f16(out, "out", m * (n // 2))
+        check(lib().fb2_gptq_linear_forward_swiglu(self._h, _stream(), x.data_ptr(), out.data_ptr(), m, 1 if x_is_sorted else 0))
+        return out
+
     def forward_host(self, x: np.ndarray, m: Optional[int] = None) -> np.ndarray:
         """The plugin call with HOST buffers (f16 numpy in, f16 numpy out); synchronous."""
         k, n = self.in_features(), self.out_features()
@@ -181,6 +217,26 @@ class GptqLinear(_LinearBase):
 
     def metadata(self):
         return self._metadata
+
+
+def fused_add_rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float, residual: Optional[torch.Tensor] = None,
+                       out: Optional[torch.Tensor] = None, out_perm: Optional[int] = None) -> torch.Tensor:
+    """fb2_fused_add_rms_norm: residual += x (in place, when given), out = rms_norm(.) * weight, optionally stored in an
+    act-order linear's column order (out_perm = GptqLinear.act_order_perm())."""
+    tokens, hidden = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().fb2_fused_add_rms_norm(_stream(), x.data_ptr(), residual.data_ptr() if residual is not None else None,
+                                       weight.data_ptr(), out.data_ptr(), tokens, hidden, float(eps), out_perm))
+    return out
+
+
+def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
+    """fb2_argmax_rows_f16: [m, n] f16 -> [m] int32."""
+    m, n = logits.shape
+    out = torch.empty((m,), dtype=torch.int32, device=logits.device)
+    check(lib().fb2_argmax_rows_f16(_stream(), logits.data_ptr(), m, n, out.data_ptr()))
+    return out
 
 
 def forward_host_batch(linears: Sequence[_LinearBase], xs: Sequence[np.ndarray], m: int,

@@ -244,6 +244,34 @@ FB2_API int fb2_fused_silu_mul_split(fb2_stream_t stream, const fb2_half *gate_u
 FB2_API int fb2_fused_gelu_tanh_mul_split(fb2_stream_t stream, const fb2_half *gate_up,
                                           fb2_half *out, size_t tokens, size_t im);
 
+/* ---- adjacent fusions: the ops on either side of the GEMMs, shaped so that no gather launch is
+ * left between them and an act-order linear.
+ *
+ * fb2_fused_add_rms_norm: residual += input (when residual != NULL; it is updated in place, as
+ * fused_add_rms_norm_inplace_f16, crates/ferrum-kernels/kernels/fused_add_rms_norm.cu:62-100), then
+ * output = rms_norm(residual or input, weight, eps) -- and, with out_perm (the device array
+ * fb2_gptq_linear_act_order_perm returns), output[:, j] = normed[:, out_perm[j]]: the activation gather of the
+ * act-order linear that follows (reference: kernels/gather_columns.cu:15, a launch of its own) rides on the norm's
+ * store; feed the result to fb2_gptq_linear_forward_sorted / _forward_swiglu(x_is_sorted = 1).
+ * f16 I/O, f32 arithmetic, hidden <= 65536. */
+FB2_API int fb2_fused_add_rms_norm(fb2_stream_t stream, const fb2_half *input, fb2_half *residual,
+                                   const fb2_half *weight, fb2_half *output, size_t tokens, size_t hidden,
+                                   float eps, const int32_t *out_perm);
+/* Device pointer to the layer's act-order column order (sorted position -> input column; K int32), or NULL when the
+ * layer reads x as it lies.  Owned by the handle. */
+FB2_API int fb2_gptq_linear_act_order_perm(const fb2_linear_t *lin, const int32_t **perm_dev);
+/* Linear::forward for activations that already are in that order. */
+FB2_API int fb2_gptq_linear_forward_sorted(const fb2_linear_t *lin, fb2_stream_t stream, const fb2_half *x_sorted,
+                                           fb2_half *y, size_t m);
+/* gate|up linear (out_features = 2 * inter, gate columns first) with SiLU(gate) * up applied in the GEMM epilogue:
+ * y [m, out_features / 2].  One launch for the reference's pair Linear::forward + fused_silu_mul_split
+ * (crates/ferrum-models/src/models/llama_family.rs:3468-3509); gate and up are rounded to f16 before the activation,
+ * as that pair does. */
+FB2_API int fb2_gptq_linear_forward_swiglu(const fb2_linear_t *lin, fb2_stream_t stream, const fb2_half *x,
+                                           fb2_half *y, size_t m, int x_is_sorted);
+/* Row argmax of f16 logits [m, n] -> out_idx [m] (ties -> lowest index; crates/ferrum-kernels/kernels/argmax_rows.cu). */
+FB2_API int fb2_argmax_rows_f16(fb2_stream_t stream, const fb2_half *logits, size_t m, size_t n, int32_t *out_idx);
+
 /* The whole MoE FFN of one layer, steps 1-6 of moe_forward_bucketed
  * (crates/ferrum-models/src/moe/dispatch.rs:1558-2192) with gather, SwiGLU and combine
  * fused around the two grouped GEMMs:
