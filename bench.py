@@ -364,6 +364,11 @@ def run_gpu(args):
                "ms_per_step": round(e_ms, 3),
                "api": "fb2_gptq_linear_forward / fb2_gptq_linear_forward_allreduce per GEMM, host <-> device copies per GEMM (per rank)"}
 
+    # ------------------------------------------------------- model-level decode step
+    model_level = None
+    if world == 1 and not args.quick:
+        model_level = run_model_level(args, fb2, lins, layers, local, series)
+
     # ------------------------------------------- Gemma3-27B TP prefill (BASELINE.json configs[4])
     tp_prefill = None
     if not args.quick and not args.no_tp_prefill:
@@ -413,6 +418,7 @@ def run_gpu(args):
                          "alg_bytes_per_launch": int(step_bytes / n_gemms)},
             "cpu_baseline": cpu, "series_decode": series, "per_shape_M1": per_shape, "prefill": prefill,
             "moe_decode": moe, "tp_prefill_gemma3": tp_prefill, "tp_allreduce": tp_allreduce, "parity": parity,
+            "model_level": model_level,
             "build_s": round(build_s, 1),
             "host_cores": os.cpu_count(),
         }
@@ -480,6 +486,57 @@ def parity_check(fb2, par, rank, world, local, comm):
     out = {k_: float(v) for k_, v in zip(sorted(out), t.tolist())}
     out["tolerance"] = 2e-3
     out["ok"] = all(v <= 2e-3 for k_, v in out.items() if k_ not in ("tolerance",))
+    return out
+
+
+def run_model_level(args, fb2, lins, layers, local, gemm_series):
+    """one CUDA graph of the Llama-3.1-8B decode step through `layers` GPTQ layers with everything but
+    attention: add+RMSNorm (storing straight into the qkv / gate|up layers' act-order column order) -> qkv -> attention
+    STUB (q is passed through: one copy kernel) -> o_proj -> add+RMSNorm -> gate|up with the SwiGLU epilogue -> down.
+    tok/s = M / step time; `gemm_share` = the same GEMMs alone (series_decode) / this step."""
+    import torch
+    dev = f"cuda:{local}"
+    H, I = LLAMA["hidden"], LLAMA["inter"]
+    out = {}
+    w_norm = torch.ones(H, device=dev, dtype=torch.float16)
+    perms = [[lins[li][j].act_order_perm() for j in range(4)] for li in range(layers)]
+    for m in (1, 4, 8, 16, 32):
+        x = torch.randn(m, H, device=dev).clamp_(-1, 1).half()
+        res = torch.zeros(m, H, device=dev, dtype=torch.float16)
+        h = torch.empty(m, H, device=dev, dtype=torch.float16)
+        qkv = torch.empty(m, 6144, device=dev, dtype=torch.float16)
+        attn = torch.empty(m, H, device=dev, dtype=torch.float16)
+        o = torch.empty(m, H, device=dev, dtype=torch.float16)
+        act = torch.empty(m, I, device=dev, dtype=torch.float16)
+        dn = torch.empty(m, H, device=dev, dtype=torch.float16)
+
+        def fn():
+            cur = x
+            for li in range(layers):
+                q_l, o_l, gu_l, d_l = lins[li]
+                fb2.fused_add_rms_norm(cur, w_norm, 1e-5, residual=res, out=h, out_perm=perms[li][0])
+                (q_l.forward_sorted if perms[li][0] else q_l.forward)(h, qkv, m)
+                attn.copy_(qkv[:, :H])                                  # attention stub
+                o_l.forward(attn, o, m)
+                fb2.fused_add_rms_norm(o, w_norm, 1e-5, residual=res, out=h, out_perm=perms[li][2])
+                gu_l.forward_swiglu(h, act, m, x_is_sorted=perms[li][2] is not None)
+                d_l.forward(act, dn, m)
+                cur = dn
+        fb2.reset_launch_count()
+        g = capture(fn)
+        launches = fb2.launch_count() // 2 + layers                    # + the stub copies (torch)
+        t = time_graph(g, 5, 3, 1) / 5                                   # ms per step of `layers` layers
+        del g
+        t32 = t * LLAMA["layers"] / layers
+        gemm_us = gemm_series.get(f"M={m}", {}).get("us_per_gemm")
+        out[f"M={m}"] = {"tok_s_no_attention": round(m / (t32 * 1e-3), 1), "ms_per_token_step_32_layers": round(t32, 4),
+                         "us_per_layer": round(t * 1e3 / layers, 2), "launches_per_layer": round(launches / layers, 2),
+                         "gemm_share": round(4 * gemm_us / (t * 1e3 / layers), 3) if gemm_us else None}
+    out["note"] = ("Llama-3.1-8B-GPTQ-Int4 decode, all 32 layers' linears + norms + SwiGLU in one CUDA graph, attention stubbed "
+                   "(q passed through), no lm_head / sampling: an upper bound of what this path allows, next to the "
+                   "reference's end-to-end serving figures on an RTX 4090 (README.md:96: 122.9 / 324.3 / 640.2 / 745.6 tok/s "
+                   "at c = 1 / 4 / 16 / 32, where the Marlin GEMMs are 73 % of the iteration, "
+                   "docs/bench/v0.2-cuda/status-2026-05-05.md:120-136)")
     return out
 
 

@@ -94,27 +94,31 @@ FB2_API size_t fb2_gptq_linear_in_features(const fb2_linear_t *lin);
 FB2_API size_t fb2_gptq_linear_out_features(const fb2_linear_t *lin);
 /* 1 when the layer was loaded with a non-trivial g_idx (quant.rs:685-711). */
 FB2_API int fb2_gptq_linear_is_act_order(const fb2_linear_t *lin);
-/* Name of the kernel family forward() will use for `m` rows ("tc-decode", "tc-prefill",
- * "generic"): introspection for tests and the bench, not a dispatch knob. */
+/* Name of the kernel family forward() will use for `m` rows ("tc-streamk": the tensor-core kernels of up to 64-row
+ * blocks -- the decode kernel of csrc/tc_decode.cuh up to 16 rows; "tc-streamk-prefill": 128 / 256-row blocks;
+ * "generic": shapes outside the tile format): introspection for tests and the bench, not a dispatch knob. */
 FB2_API const char *fb2_gptq_linear_kernel_name(const fb2_linear_t *lin, size_t m);
 
 /* Linear::forward (crates/ferrum-kernels/src/linear.rs:123; CUDA impl
  * quant_linear/cuda_marlin.rs:83-181): y[m, N] = x[m, K] . W^T (+ bias), fp16 in/out,
- * fp32 accumulate.  x and y are device pointers, row-major, contiguous.  Work is
- * appended to `stream`; no sync, no allocation.  m == 0 is a no-op. */
+ * fp32 accumulate.  x and y are device pointers, row-major, contiguous; x must be 16-byte aligned (ARG otherwise:
+ * every activation path moves 16-byte vectors).  Work is appended to `stream`; no sync, no allocation (the
+ * per-device split-K scratch grows outside graph capture only, and outgrown buffers are retired, not freed, so
+ * graphs captured earlier stay valid).  m == 0 is a no-op. */
 FB2_API int fb2_gptq_linear_forward(const fb2_linear_t *lin, fb2_stream_t stream,
                                     const fb2_half *x, fb2_half *y, size_t m);
 /* The same call for HOST buffers: copies x to the device, runs forward, copies y back
- * and synchronises.  This is the "plugin call with host buffers" the end-to-end bench
- * times; it uses a pinned staging area owned by the handle. */
+ * and synchronises; it uses a pinned staging area owned by the handle.  All host-buffer calls of one device
+ * (this one and the batch form below) are serialised by one per-device mutex: they share the split-K scratch. */
 FB2_API int fb2_gptq_linear_forward_host(fb2_linear_t *lin, const fb2_half *x_host,
                                          fb2_half *y_host, size_t m);
 
 /* Host-buffer batch form of the same call: y_host[i] = lins[i].forward(x_host[i], m) for
- * i < n (all on one device).  Inputs are staged through one pinned arena, copied to the
- * device with one transfer, the n GEMMs are enqueued back to back, outputs return with one
- * transfer, then the call synchronises.  This is what a host-side caller that owns host
- * tensors (the reference's CPU-backend tests, gptq_parity_test.rs:109-145) would call. */
+ * i < n (all on one device).  The linears are processed in chunks of 16 on three streams: the H2D copies of chunk
+ * c+1 and the D2H copies of chunk c-1 overlap the GEMMs of chunk c; page-locked caller buffers are DMA'd directly,
+ * pageable ones are staged through a pinned arena; the call returns after one synchronisation.  This is what a
+ * host-side caller that owns host tensors (the reference's CPU-backend tests, gptq_parity_test.rs:109-145) would
+ * call, and what the end-to-end bench times. */
 FB2_API int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
                                                const fb2_half *const *x_host,
                                                fb2_half *const *y_host, size_t m);
@@ -170,7 +174,8 @@ FB2_API int fb2_gptq_stack_make_expert_linear(const fb2_stack_t *st, size_t expe
 /* MarlinExpertStack::gemm_phase_batched (marlin_expert_stack.rs:64-70): for each
  * dispatch (expert, in_row, out_row, m): y[out_row .. +m, :n_per_expert] =
  * x[in_row .. +m, :K] . W_expert^T.  `dispatches` is a HOST array of nd 4-tuples of
- * int64; it is read during the call only (uploaded through a pinned ring, no sync). */
+ * int64; it is read during the call only (the entries travel by value in the kernel parameters, <= 240 per
+ * launch: no upload, no sync, graph-capturable). */
 typedef struct {
   int64_t expert, in_row, out_row, m;
 } fb2_dispatch_t;
