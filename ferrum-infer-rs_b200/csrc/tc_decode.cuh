@@ -36,35 +36,34 @@ namespace dk {
 
 enum { DK_DENSE = 0, DK_GATHER = 1, DK_ROUTED = 2 };
 
-constexpr int kNB = 16;                     // UMMA N: rows of a block (<= 16 real)
 constexpr int kWarpMma2 = 11;               // second MMA issuer: one per dequant group, so the groups are not coupled through
                                             // one in-order issue loop (the 12th warp costs no registers: 11 warps already
                                             // occupy the allocation of 12)
 constexpr int kDkThreads = 12 * 32;
 constexpr int kXSlots = 4;
-constexpr int kXBytes = kNB * 256;          // [2 atoms][16 rows][128 B]
 constexpr int kSmemBudget = 108 * 1024;     // two CTAs per SM
 // shared memory: [X slots][group exchange][barriers + misc][weight ring: run-time depth][DK_GATHER: the x rows]
-template <bool kSilu>
+// NB = UMMA N = rows of a block: 16, or 32 for the 17..32-row dense launches
+template <bool kSilu, int NB>
 struct Lay {
   static constexpr int kNacc = kSilu ? 2 : 1;
+  static constexpr int kXBytes = NB * 256;                       // [2 atoms][NB rows][128 B]
   static constexpr int kXchgBase = kXSlots * kXBytes;
-  static constexpr int kXchgBytes = kNacc * 16 * kTileN * 4;     // group <-> group exchange of partial sums
+  static constexpr int kXchgBytes = kNacc * NB * kTileN * 4;     // group <-> group exchange of partial sums
   static constexpr int kBarBase = kXchgBase + kXchgBytes;
   static constexpr int kWBase = kBarBase + 1024;
 };
 constexpr int kMinWStages = 5;
-__host__ __device__ constexpr int w_stages_for(bool silu, int xs_bytes) {
-  const int base = silu ? Lay<true>::kWBase : Lay<false>::kWBase;
+__host__ __device__ constexpr int w_stages_for(bool silu, int xs_bytes, int nb = 16) {
+  const int base = silu ? Lay<true, 16>::kWBase : (nb > 16 ? Lay<false, 32>::kWBase : Lay<false, 16>::kWBase);
   const int n = (kSmemBudget - base - xs_bytes) / kStageBytes;
   return n < kMaxWStages ? n : kMaxWStages;
 }
-static_assert(w_stages_for(true, 0) >= 7, "weight ring depth");
+static_assert(w_stages_for(true, 0) >= 7 && w_stages_for(false, 0, 32) >= 6, "weight ring depth");
 // tensor memory columns (256 allocated): A slots, per-slot accumulators, per-slot zero-point operand
 constexpr int kTmemCols = 256;
 constexpr int kColA = 0;                    // 2 slots x 64
-constexpr int kColD = 128;                  // 2 x 16: 2^-24 * sum_k (q_k - z) x_k
-constexpr int kColZ = 160;                  // 2 x 8 columns of half2(-z, -z) * 2^-24
+constexpr int kColD = 128;                  // 2 x NB: 2^-24 * sum_k (q_k - z) x_k; behind it 2 x 8 columns of half2(-z, -z) * 2^-24
 enum { BAR_FULL_W = 0, BAR_EMPTY_W = kMaxWStages, BAR_FULL_X = 2 * kMaxWStages, BAR_EMPTY_X = BAR_FULL_X + kXSlots,
        BAR_FULL_A = BAR_EMPTY_X + kXSlots, BAR_DONE = BAR_FULL_A + 2, BAR_XS = BAR_DONE + 2, BAR_COUNT = BAR_XS + 1 };
 static_assert(BAR_COUNT * 8 <= 512, "barrier area too small");
@@ -153,9 +152,13 @@ __device__ __forceinline__ Plan make_plan_dev(const TcParams &p) {
 template <int R, int kMode, bool kSilu, bool kPush>
 __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "rows per thread");
-  static_assert(!(kSilu && kPush) && !(kPush && kMode == DK_ROUTED), "combination not instantiated");
-  using L = Lay<kSilu>;
+  static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "rows per thread");
+  constexpr int kNB = R > 16 ? 32 : 16;             // UMMA N
+  constexpr int kColZ = kColD + 2 * kNB;
+  static_assert(kColZ + 16 <= kTmemCols, "tensor memory map");
+  static_assert(!(kSilu && kPush) && !(kPush && kMode == DK_ROUTED) && !(kSilu && R > 8), "combination not instantiated");
+  using L = Lay<kSilu, kNB>;
+  constexpr int kXBytes = L::kXBytes;
   constexpr int NACC = L::kNacc;
   constexpr int SX = kXSlots;
   constexpr bool kRouted = kMode == DK_ROUTED, kGather = kMode == DK_GATHER;
@@ -468,15 +471,19 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       ptx::tc_fence_after();
     };
     auto fold = [&]() {
-      uint32_t dv[R];
-      tmem_ld_rows<R>(k_d, dv);
-      ptx::tmem_wait_ld();
-      if (NACC == 2 && pend_up) {
+      constexpr int RC = R > 16 ? 16 : R;           // columns per tcgen05.ld (R = 32: two halves, 16 fewer live registers)
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[NACC - 1][r] = fmaf(sc_prev, __uint_as_float(dv[r]), acc[NACC - 1][r]);
-      } else {
+      for (int c0 = 0; c0 < R; c0 += RC) {
+        uint32_t dv[RC];
+        tmem_ld_rows<RC>(k_d + c0, dv);
+        ptx::tmem_wait_ld();
+        if (NACC == 2 && pend_up) {
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[0][r] = fmaf(sc_prev, __uint_as_float(dv[r]), acc[0][r]);
+          for (int r = 0; r < RC; r++) acc[NACC - 1][c0 + r] = fmaf(sc_prev, __uint_as_float(dv[r]), acc[NACC - 1][c0 + r]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < RC; r++) acc[0][c0 + r] = fmaf(sc_prev, __uint_as_float(dv[r]), acc[0][c0 + r]);
+        }
       }
     };
     // one 64-k half: two LDS.128 -> 16 lo-class + 16 hi-class half2 registers
@@ -535,11 +542,11 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
         if constexpr (R <= 4) {
           if (s == 1) {
 #pragma unroll
-            for (int r = 0; r < R; r++) xc[(a * 16 + r) * kTileN + nl] = acc[a][r];
+            for (int r = 0; r < R; r++) xc[(a * kNB + r) * kTileN + nl] = acc[a][r];
           }
         } else {
 #pragma unroll
-          for (int jj = 0; jj < OWN; jj++) xc[(a * 16 + (1 - s) * OWN + jj) * kTileN + nl] = acc[a][(1 - s) * OWN + jj];
+          for (int jj = 0; jj < OWN; jj++) xc[(a * kNB + (1 - s) * OWN + jj) * kTileN + nl] = acc[a][(1 - s) * OWN + jj];
         }
       }
       ptx::named_bar_sync(1, kDequantWarps * 32);
@@ -549,7 +556,7 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
 #pragma unroll
       for (int a = 0; a < NACC; a++) {
 #pragma unroll
-        for (int jj = 0; jj < OWN; jj++) v[a][jj] = (has_rows ? acc[a][rb + jj] + xc[(a * 16 + rb + jj) * kTileN + nl] : 0.f);
+        for (int jj = 0; jj < OWN; jj++) v[a][jj] = (has_rows ? acc[a][rb + jj] + xc[(a * kNB + rb + jj) * kTileN + nl] : 0.f);
 #pragma unroll
         for (int r = 0; r < R; r++) acc[a][r] = 0.f;
       }
@@ -564,7 +571,7 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       const bool owner = !whole && cta == c_first;
       // flag-in-value exchange: the slot area of a CTA, [2 accumulators][8 rows][128], holds either pair of 8-row
       // accumulators or the 16 rows of one
-      const bool ll = !whole && NACC * R <= 16 && G <= p.ll_ctas;
+      const bool ll = !whole && NACC * R <= 16 && G <= p.ll_ctas;   // (R = 32: partial tiles + counter)
       const int nr = nv - rb;                                    // real rows among this group's: j < nr
       auto store_out = [&](int row_in_block, float v0, float v1) {
         int cr;

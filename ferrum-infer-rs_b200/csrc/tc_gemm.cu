@@ -1062,7 +1062,11 @@ int launch_dk_rows(int m, const TcPlan &pl, cudaStream_t stream, const TcParams 
   return m <= 1 ? launch_dk<1, kMode, false, kPush>(pl, stream, p, xmap)
          : m <= 2 ? launch_dk<2, kMode, false, kPush>(pl, stream, p, xmap)
          : m <= 4 ? launch_dk<4, kMode, false, kPush>(pl, stream, p, xmap)
-         : m <= 8 ? launch_dk<8, kMode, false, kPush>(pl, stream, p, xmap) : launch_dk<16, kMode, false, kPush>(pl, stream, p, xmap);
+         : m <= 8 ? launch_dk<8, kMode, false, kPush>(pl, stream, p, xmap)
+         : launch_dk<16, kMode, false, kPush>(pl, stream, p, xmap);
+  // (a 32-row instantiation exists in tc_decode.cuh -- R = 32, UMMA N = 32 -- and was measured: 16.6 / 16.2 / 29.4 /
+  // 23.8 us on the four Llama shapes at M = 32 against 13.5 / 13.1 / 23.9 / 21.4 us of tc_body<32>: 32 running sums per
+  // thread spill, and the per-unit accumulator read-out grows with the rows.  Not instantiated.)
 }
 
 template <int NB>
@@ -1089,7 +1093,7 @@ static bool dk_eligible(const WeightRef &w, const RowMap &rows, const DispatchTa
 bool dk_gather_ok(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue) {
   static const bool no_gather = [] { const char *e = getenv("FB2_DEBUG_NO_DK_GATHER"); return e && e[0] == '1'; }();
   return !no_gather && w.perm && dk_eligible(w, rows, tbl, epilogue) && w.k % 8 == 0 &&
-         dk::w_stages_for(epilogue != 0, rows.m * w.k * 2) >= dk::kMinWStages;
+         rows.m <= 16 && dk::w_stages_for(epilogue != 0, rows.m * w.k * 2) >= dk::kMinWStages;
 }
 // ... and the routed blocks of an expert stack when they hold at most 8 rows (16 without the SwiGLU epilogue behind
 // FB2_DEBUG_DK_ROUTED_MAXBLOCK=16)
@@ -1284,7 +1288,7 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
            : pushing ? launch_dk_rows<dk::DK_GATHER, true>(rows.m, pl, stream, p, xmap)
                      : launch_dk_rows<dk::DK_GATHER, false>(rows.m, pl, stream, p, xmap);
     } else {
-      p.w_stages = dk::w_stages_for(epilogue != 0, 0);
+      p.w_stages = dk::w_stages_for(epilogue != 0, 0, nb);
       rc = epilogue ? launch_dk_rows_silu<dk::DK_DENSE>(rows.m, pl, stream, p, xmap)
            : pushing ? launch_dk_rows<dk::DK_DENSE, true>(rows.m, pl, stream, p, xmap)
                      : launch_dk_rows<dk::DK_DENSE, false>(rows.m, pl, stream, p, xmap);
