@@ -148,6 +148,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void *tmap,
       ::"r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same box delivered to the same shared-memory offset of every CTA of the cluster named in cta_mask; each
+// destination's mbarrier (same offset) receives the complete_tx of the bytes it got.
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst_smem, const void *tmap, int c0, int c1, uint32_t bar,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// MMA completion -> one arrival on the mbarrier at this offset in EVERY CTA of cta_mask
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const void *tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

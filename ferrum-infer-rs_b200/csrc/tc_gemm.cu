@@ -71,14 +71,16 @@ template <int NB>
 struct StageCfg {
   static constexpr bool kWide = NB >= 128;
   static constexpr int kCtasPerSm = kWide ? 1 : 2;
+  static constexpr int kDequantWarps = kWide ? 16 : 8;          // two teams of eight in the one-CTA-per-SM class
+  static constexpr int kCtaThreads = (kDequantWarps + 3) * 32;
   // Registers are allocated per warp in groups of four warps: a 10-warp CTA occupies the register
   // space of 12, so two CTAs are co-resident only below 65536 / (2 * 12 * 32) = 85 registers per
   // thread.  Declaring 384 threads to the compiler makes it hold that budget (80); the launch still
   // uses kThreads.  (At 96 registers the occupancy query answers ONE CTA per SM.)
 #ifdef FB2_REGS96
-  static constexpr int kBoundThreads = kThreads;
+  static constexpr int kBoundThreads = kCtaThreads;
 #else
-  static constexpr int kBoundThreads = kWide ? kThreads : 384;
+  static constexpr int kBoundThreads = kWide ? kCtaThreads : 384;
 #endif
   static constexpr int kTmemCols = kWide ? 512 : 256;
   static constexpr int kTmemABase = kWide ? 256 : 128;
@@ -258,22 +260,38 @@ __device__ __forceinline__ long long fb2_gtime() { long long t; asm volatile("mo
 // push branches in the epilogue cost the prefill variant 13 % when they were a run-time test.
 #define push_world(p) (kPush ? (p).push.world : 0)
 
-template <int NB, bool kSilu, bool kPush = false>
+// kPair (prefill row blocks only): the grid is launched in CLUSTERS OF TWO.  The two CTAs of a cluster walk the same unit
+// sequence on two ADJACENT weight tiles, so they need the same activation slices at the same time: each loads half of
+// every slice (NB / 2 rows) and multicasts it to both, which halves the L2 -> SM traffic of the operand that bounded
+// the tensor pipe at 51 % in round 1 (64 KB of activations per 8.7 KB weight stage, re-read by every tile).
+template <int NB, bool kSilu, bool kPush = false, bool kPair = false>
 __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *tbl, const CUtensorMap *xmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using SC = StageCfg<NB>;
   constexpr int NACC = kSilu ? 2 : 1;
   constexpr int kTmemCols = SC::kTmemCols, kTmemABase = SC::kTmemABase, kASlots = SC::kASlots;
-  constexpr int HALF = NB / 2;
+  // Dequant warps come in TEAMS of eight (four TMEM lane quarters x two 64-k halves).  The prefill classes run two
+  // teams that take alternate units, so two units are in flight per CTA (round 1's one-team loop was latency-bound:
+  // 30 % issue utilisation at 51 % tensor pipe) -- 19 warps still fit the register file of the one-CTA-per-SM class.
+  constexpr int DW = SC::kDequantWarps, kTeams = DW / 8;
+  constexpr int kWarpW = DW, kWarpMma = DW + 1, kWarpX = DW + 2, kThreads = (DW + 3) * 32;
+  constexpr int kDequantWarps = DW;
+  constexpr int HALF = NB / (DW / 4);                            // rows each set of four epilogue warps handles
   constexpr int SW = SC::kWStages, SX = SC::kXSlots;
   static_assert(SW >= 3 && SX >= 2, "smem rings too shallow");
   static_assert(NACC * NB <= kTmemABase, "accumulators overlap the A ring");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FB2_TL(0);
-  int G = (int)gridDim.x;                                        // CTAs that take part (see below)
-  const int cta = (int)blockIdx.x;
-  const int groups = p.groups, n_tiles = p.n_tiles;
+  static_assert(!kPair || (NB >= 128 && !kSilu && !kPush), "paired CTAs: prefill row blocks only");
+  // Scheduling view: in paired mode the stream-K bookkeeping runs over PAIRS (pair index, tile pairs); this CTA's
+  // physical tile is 2 * tile + crank and its scratch slots are indexed by the physical CTA.
+  const int crank = kPair ? (int)(blockIdx.x & 1u) : 0;
+  int G = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;       // scheduling CTAs that take part (see below)
+  const int cta = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  auto phys_cta = [&](int c) { return kPair ? 2 * c + crank : c; };
+  auto phys_tile = [&](int t) { return kPair ? 2 * t + crank : t; };
+  const int groups = p.groups, n_tiles = kPair ? p.n_tiles / 2 : p.n_tiles;
   const int upt = NACC * groups;                                 // units per output tile
   // Routed mode learns its block count from the align kernel (an earlier kernel): its unit range
   // is computed after the grid dependency, i.e. after the dependency-free part of the setup.
@@ -305,7 +323,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     if (lane == 0) {
       for (int i = 0; i < SW; i++) {
         ptx::mbar_init(bar(BAR_FULL_W + i), 1);                  // the producer's arrive.expect_tx
-        ptx::mbar_init(bar(BAR_EMPTY_W + i), kDequantWarps);     // read into registers by all 8 warps
+        ptx::mbar_init(bar(BAR_EMPTY_W + i), 8);                 // read into registers by the 8 warps of one team
       }
       ptx::mbar_fence_init();
     }
@@ -316,7 +334,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       for (int i = 0; i < SX; i++) {
         // one arrive.expect_tx by the producer (+ 32 cp.async arrivals when rows are gathered)
         ptx::mbar_init(bar(BAR_FULL_X + i), (p.x_tma & 1) ? 1 : 1 + 32);
-        ptx::mbar_init(bar(BAR_EMPTY_X + i), 1);                 // the MMA commit
+        ptx::mbar_init(bar(BAR_EMPTY_X + i), kPair ? 2 : 1);     // the MMA commit (paired: of both CTAs, which both write it)
       }
       ptx::mbar_fence_init();
     }
@@ -363,7 +381,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   auto weight_src = [&](int blk, int tile, int phase, int g) {
       const int expert = rowmap_block_expert(p.rm, tbl, blk);
       return p.w.tiles +
-             ((size_t)expert * p.tiles_per_expert + p.w.col0 / kTileN + tile + (size_t)phase * n_tiles) *
+             ((size_t)expert * p.tiles_per_expert + p.w.col0 / kTileN + phys_tile(tile) + (size_t)phase * p.n_tiles) *
                tile_stride + (size_t)g * kStageBytes;
   };
   uint32_t tmem_base = 0;
@@ -372,6 +390,12 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     ptx::named_bar_sync(2, kThreads);
     ptx::tc_fence_after();
     tmem_base = *s_tmem;
+  }
+  if constexpr (kPair) {
+    // the peer multicasts into this CTA's slots and arrives on its barriers: both CTAs' barriers must be initialised
+    // before either starts (and, at the end, neither may exit while the other can still reach it)
+    __syncthreads();
+    ptx::cluster_sync_all();
   }
   FB2_TL(1);
   FB2_TLV(8, u1 - u0);
@@ -452,8 +476,16 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
             ptx::mbar_arrive_expect_tx(full, (p.x_tma & 1) ? (uint32_t)SC::kXBytes : 0u);
             if (p.x_tma & 1) {
               // [NB rows x 64 k] boxes, hardware 128B swizzle; rows past the tensor end read as zero
-              ptx::tma_load_2d(slot_addr, xmap, g * kGroup, row0, full);
-              ptx::tma_load_2d(slot_addr + NB * 128, xmap, g * kGroup + 64, row0, full);
+              if constexpr (kPair) {
+                // this CTA's half of the rows, delivered to both CTAs of the pair (the tensor map's box is NB / 2 rows)
+                const uint32_t half_off = (uint32_t)crank * (NB / 2) * 128u;
+                ptx::tma_load_2d_multicast(slot_addr + half_off, xmap, g * kGroup, row0 + crank * (NB / 2), full, (uint16_t)3);
+                ptx::tma_load_2d_multicast(slot_addr + NB * 128 + half_off, xmap, g * kGroup + 64, row0 + crank * (NB / 2), full,
+                                           (uint16_t)3);
+              } else {
+                ptx::tma_load_2d(slot_addr, xmap, g * kGroup, row0, full);
+                ptx::tma_load_2d(slot_addr + NB * 128, xmap, g * kGroup + 64, row0, full);
+              }
             }
           }
           __syncwarp();
@@ -513,7 +545,10 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
                 ptx::umma_f16_ts(d_tmem, a_t + kk * 8, b_d + (uint64_t)(kk * 2), idesc,
                                  (h | kk) != 0 ? 1u : acc_flag);
               ptx::tc_commit(bar(BAR_EMPTY_A + ap.st * 2 + h));
-              if (h == 1) ptx::tc_commit(bar(BAR_EMPTY_X + xp.st)); // activation slot consumed
+              if (h == 1) {                                          // activation slot consumed
+                if constexpr (kPair) ptx::tc_commit_multicast(bar(BAR_EMPTY_X + xp.st), (uint16_t)3);
+                else ptx::tc_commit(bar(BAR_EMPTY_X + xp.st));
+              }
             }
             __syncwarp();
           }
@@ -526,7 +561,9 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   } else {
     // ======================================================== dequant + epilogue warps
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int h = warp >> 2;              // which 64-k half of every group this warp owns
+    const int h = (warp >> 2) & 1;        // which 64-k half of every group this warp owns
+    const int team = warp >> 3;           // which units this warp converts: local unit index % kTeams
+    const int rset = warp >> 2;           // which rows of the block this warp finishes in the epilogue
     const int nl = q * 32 + lane;         // weight column inside the tile == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t w_off = SC::kWBase + (uint32_t)h * 4096u + (uint32_t)nl * 16u;    // chunks 2h, 2h+1
@@ -541,7 +578,8 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
     k_ta = __shfl_sync(0xffffffffu, k_ta, lane); k_bf = __shfl_sync(0xffffffffu, k_bf, lane);
     k_be = __shfl_sync(0xffffffffu, k_be, lane); k_fw = __shfl_sync(0xffffffffu, k_fw, lane);
     k_ew = __shfl_sync(0xffffffffu, k_ew, lane);
-    RingPos wp{0, 0}, ap{0, 0};
+    RingPos wp{team, 0}, ap{team, 0};     // this team's next unit is local unit `team`
+    u32 lunit = 0;                        // local index of the next unit of the range (all teams count all units)
     int seg = 0;
     ptx::grid_dependency_wait();          // before the first global write / scratch access
     FB2_TL(2);
@@ -609,12 +647,19 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         }
       } else {
 #pragma unroll 1
-        for (int n = sg.r1 - sg.r0; n > 0; n--, ap.advance(kASlots)) unit(std::integral_constant<int, -1>{});
+        for (int n = sg.r1 - sg.r0; n > 0; n--, lunit++) {
+          if (kTeams > 1 && (lunit % (u32)kTeams) != (u32)team) continue;   // the other team's unit
+          unit(std::integral_constant<int, -1>{});                          // (advances the weight ring once)
+#pragma unroll
+          for (int t = 1; t < kTeams; t++) wp.advance(SW);
+#pragma unroll
+          for (int t = 0; t < kTeams; t++) ap.advance(kASlots);
+        }
       }
 
       // ------------------------------------------------ epilogue of this tile segment
       const int r_begin = sg.r0, r_end = sg.r1;                  // [r_begin, r_end) of [0, upt)
-      const int blk = sg.blk, tile = sg.tile, tau = sg.blk * n_tiles + sg.tile;
+      const int blk = sg.blk, tile = phys_tile(sg.tile), tau = sg.blk * p.n_tiles + tile;   // physical tile / counter index
       FB2_TL(4);
       // Everything that does not need the accumulator is resolved while the last MMAs drain.
       // Real rows of this block: they form a prefix (dense: m; dispatch: entry.m; routed:
@@ -648,7 +693,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
       // tile is the FIRST segment of their range) publish a partial and never stall in mid-stream.
       int c_first = cta, c_last = cta;
       if (!whole) {
-        const u32 tile_u0 = (u32)tau * (u32)upt;
+        const u32 tile_u0 = (u32)(sg.blk * n_tiles + sg.tile) * (u32)upt;      // in scheduling units
         c_first = cta_of_unit(tile_u0, T, G);
         c_last = cta_of_unit(tile_u0 + upt - 1, T, G);
       }
@@ -677,7 +722,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
         // sets (any warp may read any accumulator COLUMN of its lane quarter), so eight rows still take
         // a single polling round.
 #pragma unroll 1
-        for (int jr = h * kLlGroup; jr < nv; jr += 2 * kLlGroup) {   // warp-uniform loop bounds
+        for (int jr = rset * kLlGroup; jr < nv; jr += 2 * kLlGroup) {   // warp-uniform loop bounds
           const int nr = nv - jr;                                // rows of this group: j < nr
           float v[NACC][kLlGroup];
 #pragma unroll
@@ -695,7 +740,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
             }
           }
           auto slot_of = [&](int c, int a, int j) {
-            return p.ll + (size_t)c * kLlFloatsPerCta + (size_t)((a * kLlRows + jr + j) * kTileN + nl);
+            return p.ll + (size_t)phys_cta(c) * kLlFloatsPerCta + (size_t)((a * kLlRows + jr + j) * kTileN + nl);
           };
           if (!owner) {
 #pragma unroll
@@ -777,25 +822,25 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
           __syncwarp();                                            // reconverge before .sync.aligned tcgen05.ld
           ptx::named_bar_sync(1, kDequantWarps * 32);
         }
-        float *part = p.partials + (size_t)cta * kPart;
+        float *part = p.partials + (size_t)phys_cta(cta) * kPart;
         // The accumulator is read in chunks of CH columns (activation rows) so that the same code
         // serves NB = 16 ... 256 without holding NB/2 floats per thread.
 #pragma unroll 1
         for (int ch = 0; ch < NCH; ch++) {
-          const int nvc = nv - (h * HALF + ch * CH);               // real rows of this chunk (warp-uniform)
+          const int nvc = nv - (rset * HALF + ch * CH);               // real rows of this chunk (warp-uniform)
           if (nvc <= 0) break;                                     // a prefix: later chunks are empty too
           float v[NACC][CH];
 #pragma unroll
           for (int a = 0; a < NACC; a++) {
             const bool touched = r_begin < (a + 1) * groups && r_end > a * groups;   // CTA-uniform
             if (touched) {
-              load_acc_chunk<CH>(lane_base + a * NB + h * HALF + ch * CH, v[a]);
+              load_acc_chunk<CH>(lane_base + a * NB + rset * HALF + ch * CH, v[a]);
             } else {
 #pragma unroll
               for (int j = 0; j < CH; j++) v[a][j] = 0.0f;
             }
           }
-          const size_t row_off = (size_t)(h * HALF + ch * CH) * kTileN + nl;
+          const size_t row_off = (size_t)(rset * HALF + ch * CH) * kTileN + nl;
           if (owner) {
             // UC contributors x CH rows x NACC accumulators of independent L2 loads in flight; the sums
             // are taken in contributor order (deterministic)
@@ -805,7 +850,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
               float t[UC][NACC][CH];
 #pragma unroll
               for (int i = 0; i < UC; i++) {
-                const float *src = p.partials + (size_t)(c0 + i) * kPart + row_off;
+                const float *src = p.partials + (size_t)phys_cta(c0 + i) * kPart + row_off;
 #pragma unroll
                 for (int a = 0; a < NACC; a++)
 #pragma unroll
@@ -823,7 +868,7 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
           if (whole || owner) {
 #pragma unroll
             for (int j = 0; j < CH; j++)
-              if (j < nvc) store_out(h * HALF + ch * CH + j, v[0][j], v[NACC - 1][j]);
+              if (j < nvc) store_out(rset * HALF + ch * CH + j, v[0][j], v[NACC - 1][j]);
           } else {
 #pragma unroll
             for (int a = 0; a < NACC; a++)
@@ -858,15 +903,16 @@ __device__ __forceinline__ void tc_body(const TcParams &p, const DispatchTable *
   // -------------------------------------------------------------------------- teardown
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync_all();                  // the peer no longer reaches this CTA's memory
   if (warp == kWarpMma) ptx::tmem_dealloc<kTmemCols>(tmem_base);
   FB2_TL(7);
 }
 
-template <int NB, bool kSilu, bool kPush = false>
+template <int NB, bool kSilu, bool kPush = false, bool kPair = false>
 __global__ void __launch_bounds__(StageCfg<NB>::kBoundThreads, StageCfg<NB>::kCtasPerSm)
 tc_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap xmap) {
   ptx::launch_dependents();
-  tc_body<NB, kSilu, kPush>(p, nullptr, &xmap);
+  tc_body<NB, kSilu, kPush, kPair>(p, nullptr, &xmap);
 }
 template <int NB>
 __global__ void __launch_bounds__(StageCfg<NB>::kBoundThreads, StageCfg<NB>::kCtasPerSm)
@@ -932,6 +978,7 @@ struct TcPlan {
   long long units;
   size_t partial_floats, counters;
   uint32_t smem;
+  int paired;             // prefill row blocks: clusters of two CTAs on adjacent tiles (tc_body kPair)
 };
 
 int pick_nb(int rows_per_block, bool allow_wide) {
@@ -968,7 +1015,16 @@ TcPlan make_plan(const WeightRef &w, const RowMap &rows, int epilogue, int sm_co
   const int slots = per_sm * (sm_count > 0 ? sm_count : 148);
   const int upt = pl.nacc * (w.k / kGroup);
   static const bool no_align = [] { const char *e = getenv("FB2_DEBUG_NO_TILE_ALIGN"); return e && e[0] == '1'; }();
-  const GridPlan gp = plan_grid(units, upt, slots, rows.mode == ROWS_ROUTED, !no_align);   // sched.cuh
+  static const bool no_pair = [] { const char *e = getenv("FB2_DEBUG_NO_PAIR"); return e && e[0] == '1'; }();
+  pl.paired = !no_pair && pl.nb >= 128 && rows.mode == ROWS_DENSE && !epilogue && pl.n_tiles % 2 == 0 && slots >= 2;
+  GridPlan gp;
+  if (pl.paired) {
+    // schedule PAIRS: half the tiles (tile pairs), half the slots; the grid is twice the number of scheduling CTAs
+    gp = plan_grid(units / 2, upt, slots / 2, false, !no_align);
+    gp.grid *= 2;
+  } else {
+    gp = plan_grid(units, upt, slots, rows.mode == ROWS_ROUTED, !no_align);   // sched.cuh
+  }
   pl.whole_tiles = gp.whole_tiles;
   pl.grid = gp.grid;
   pl.partial_floats = (size_t)pl.grid * pl.nacc * pl.nb * kTileN;
@@ -1018,7 +1074,7 @@ int make_x_tensor_map(CUtensorMap *map, const __half *x, size_t rows, size_t k, 
 void launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, const TcPlan &pl, cudaStream_t stream) {
   cfg = cudaLaunchConfig_t{};
   cfg.gridDim = dim3((unsigned)pl.grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(pl.nb >= 128 ? StageCfg<256>::kCtaThreads : kThreads);
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = stream;
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1027,6 +1083,22 @@ void launch_cfg(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, const TcPlan
   cfg.numAttrs = 1;
 }
 
+template <int NB>
+int launch_paired(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(tc_gemm_kernel<NB, false, false, true>,
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of<NB>());
+  FB2_CUDA_TRY(attr_rc);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  launch_cfg(cfg, attr, pl, stream);
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.numAttrs = 2;
+  FB2_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<NB, false, false, true>, p, xmap));
+  return FB2_OK;
+}
 template <int NB, bool kSilu, bool kPush = false>
 int launch_plain(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
   FB2_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<NB, kSilu, kPush>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
@@ -1233,7 +1305,7 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
       return FB2_ERR_ARG;
     }
   } else if (rows.mode != ROWS_ROUTED && x_rows > 0 && ((uintptr_t)x % 16) == 0) {
-    int rc = make_x_tensor_map(&xmap, x, x_rows, (size_t)w.k, nb);
+    int rc = make_x_tensor_map(&xmap, x, x_rows, (size_t)w.k, pl.paired ? nb / 2 : nb);   // paired CTAs load half a block each
     if (rc) return rc;
     p.x_tma = 1;
   } else if (nb > 64) {
@@ -1310,7 +1382,8 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
     rc = nb == 16 ? launch_plain<16, false>(pl, stream, p, xmap)
          : nb == 32 ? launch_plain<32, false>(pl, stream, p, xmap)
          : nb == 64 ? launch_plain<64, false>(pl, stream, p, xmap)
-         : nb == 128 ? launch_plain<128, false>(pl, stream, p, xmap) : launch_plain<256, false>(pl, stream, p, xmap);
+         : nb == 128 ? (pl.paired ? launch_paired<128>(pl, stream, p, xmap) : launch_plain<128, false>(pl, stream, p, xmap))
+                     : (pl.paired ? launch_paired<256>(pl, stream, p, xmap) : launch_plain<256, false>(pl, stream, p, xmap));
   }
   if (rc) return rc;
   count_launch();
