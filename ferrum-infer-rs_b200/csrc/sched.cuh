@@ -48,6 +48,11 @@ constexpr int kWholeTileMaxUnits = 8;
 FB2_HD bool whole_tile_mode(int upt, long long n_tiles_total, int slots) {
   return upt <= kWholeTileMaxUnits && (n_tiles_total <= slots || n_tiles_total >= 4LL * slots);
 }
+// Prefill row blocks (128 / 256 rows): a partial tile is 64 / 128 KB of fp32 per contributor, so a launch whose tiles
+// nearly fill the grid one-to-one keeps them whole whatever their length.
+FB2_HD bool whole_tile_mode_wide(long long n_tiles_total, int slots) {
+  return n_tiles_total <= slots && n_tiles_total * 5 >= slots * 4LL;
+}
 FB2_HD u32 tile_range_start(u32 c, u32 NT, u32 G, u32 upt) { return (c * NT / G) * upt; }
 FB2_HD int cta_of_unit(u32 u, u32 T, u32 G) {
   u32 c = u * G / T;
@@ -106,9 +111,9 @@ struct SegIter {
 struct GridPlan {
   int grid, whole_tiles;
 };
-FB2_HD GridPlan plan_grid(long long units, int upt, int slots, bool routed, bool tile_align) {
+FB2_HD GridPlan plan_grid(long long units, int upt, int slots, bool routed, bool tile_align, bool wide = false) {
   GridPlan gp;
-  gp.whole_tiles = !routed && whole_tile_mode(upt, units / upt, slots);
+  gp.whole_tiles = !routed && (whole_tile_mode(upt, units / upt, slots) || (wide && whole_tile_mode_wide(units / upt, slots)));
   long long g = gp.whole_tiles ? units / upt : units / 2;         // whole tiles | >= 2 units per CTA
   if (g < 1) g = 1;
   gp.grid = (int)(g < slots ? g : slots);

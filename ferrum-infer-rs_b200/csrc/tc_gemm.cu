@@ -985,6 +985,8 @@ int pick_nb(int rows_per_block, bool allow_wide) {
   if (rows_per_block <= 16) return 16;
   if (rows_per_block <= 32) return 32;
   if (rows_per_block <= 64 || !allow_wide) return 64;
+  static const int force = [] { const char *e = getenv("FB2_DEBUG_WIDE_NB"); return e ? atoi(e) : 0; }();
+  if (force == 128 || force == 256) return force;
   return rows_per_block <= 128 ? 128 : 256;
 }
 
@@ -1014,16 +1016,28 @@ TcPlan make_plan(const WeightRef &w, const RowMap &rows, int epilogue, int sm_co
   const int per_sm = ctas_per_sm_dbg ? ctas_per_sm_dbg : (pl.nb >= 128 ? 1 : 2);
   const int slots = per_sm * (sm_count > 0 ? sm_count : 148);
   const int upt = pl.nacc * (w.k / kGroup);
+  // A prefill batch over a narrow layer (Llama o_proj / down_proj at M = 512: 32 tiles): 128-row blocks give one whole
+  // tile per CTA -- no split tiles, whose partials are 128 KB each at 256 rows (o_proj: 26.2 -> 19.6 us).
+  if (rows.mode == ROWS_DENSE && pl.nb == 256 && !epilogue) {
+    static const bool forced = getenv("FB2_DEBUG_WIDE_NB") != nullptr;
+    const long long nt128 = (long long)((rows.m + 127) / 128) * pl.n_tiles;
+    if (!forced && whole_tile_mode_wide(nt128, slots)) {
+      pl.nb = 128;
+      pl.row_blocks = (rows.m + 127) / 128;
+    }
+  }
+  const long long units2 = (long long)pl.row_blocks * pl.n_tiles * pl.nacc * (w.k / kGroup);
+  pl.units = units2;
   static const bool no_align = [] { const char *e = getenv("FB2_DEBUG_NO_TILE_ALIGN"); return e && e[0] == '1'; }();
   static const bool no_pair = [] { const char *e = getenv("FB2_DEBUG_NO_PAIR"); return e && e[0] == '1'; }();
   pl.paired = !no_pair && pl.nb >= 128 && rows.mode == ROWS_DENSE && !epilogue && pl.n_tiles % 2 == 0 && slots >= 2;
   GridPlan gp;
   if (pl.paired) {
     // schedule PAIRS: half the tiles (tile pairs), half the slots; the grid is twice the number of scheduling CTAs
-    gp = plan_grid(units / 2, upt, slots / 2, false, !no_align);
+    gp = plan_grid(pl.units / 2, upt, slots / 2, false, !no_align, true);
     gp.grid *= 2;
   } else {
-    gp = plan_grid(units, upt, slots, rows.mode == ROWS_ROUTED, !no_align);   // sched.cuh
+    gp = plan_grid(pl.units, upt, slots, rows.mode == ROWS_ROUTED, !no_align, pl.nb >= 128);   // sched.cuh
   }
   pl.whole_tiles = gp.whole_tiles;
   pl.grid = gp.grid;
@@ -1245,6 +1259,7 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
     return FB2_ERR_ARG;
   }
   TcPlan pl = make_plan(w, rows, epilogue, sm_count);
+  nb = pl.nb;                                  // (make_plan may choose narrower prefill row blocks than plan_rows)
   // the kernels' unit bookkeeping is 32-bit: units x CTAs stays below 2^31
   // (FB2_DEBUG_MAX_UNIT_CTAS lowers the limit so that a test can reach the chunked path with a small batch)
   static const long long unit_cta_limit = [] {
