@@ -121,6 +121,11 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void *src
       : "memory");
 }
 // Bulk prefetch global -> L2 (no destination, no completion signal).
+// warpgroup register reallocation (all four warps of a warpgroup execute the same instruction)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }

@@ -243,6 +243,12 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
   { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); FB2_TLV(10, smid); }
 #endif
 
+  // Warps 8..11 (weight / activation producers, MMA issuers) form one warpgroup and need few registers; the two dequant
+  // warpgroups take what they release: 48 + 2 x 96 = 3 x 80 per thread, and the running sums, the unit being converted and
+  // the routed bookkeeping stay in registers (at 80 the routed variants spilled loop-carried state to local memory, which
+  // does not fit the ~24 KB of L1 this kernel's shared memory leaves: every spill load was an L2 round trip in the unit loop).
+  if (warp >= kDequantWarps) {
+  ptx::setmaxnreg_dec<48>();
   if (warp == kWarpW) {
     // ========================================================== weight producer (HBM stream)
     // Weights depend on no earlier kernel: under programmatic dependent launch this warp streams ahead of
@@ -427,7 +433,9 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       }
       __syncwarp();
     }
+  }
   } else {
+    ptx::setmaxnreg_inc<96>();
     // ======================================================== dequant + accumulate + epilogue warps
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int s = warp >> 2;              // group: A slot / accumulator, parity of the units it takes
@@ -545,8 +553,11 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
             for (int r = 0; r < R; r++) xc[(a * kNB + r) * kTileN + nl] = acc[a][r];
           }
         } else {
+          // (selects between compile-time indices: a run-time index would move the running sums to local memory, and the
+          // deferred epilogue inside the unit loop would then write them through on every unit)
 #pragma unroll
-          for (int jj = 0; jj < OWN; jj++) xc[(a * kNB + (1 - s) * OWN + jj) * kTileN + nl] = acc[a][(1 - s) * OWN + jj];
+          for (int jj = 0; jj < OWN; jj++)
+            xc[(a * kNB + (1 - s) * OWN + jj) * kTileN + nl] = s ? acc[a][jj] : acc[a][OWN + jj];
         }
       }
       ptx::named_bar_sync(1, kDequantWarps * 32);
@@ -556,7 +567,10 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
 #pragma unroll
       for (int a = 0; a < NACC; a++) {
 #pragma unroll
-        for (int jj = 0; jj < OWN; jj++) v[a][jj] = (has_rows ? acc[a][rb + jj] + xc[(a * kNB + rb + jj) * kTileN + nl] : 0.f);
+        for (int jj = 0; jj < OWN; jj++) {
+          const float mine = (R > 4 && s) ? acc[a][(R > 4 ? OWN : 0) + jj] : acc[a][jj];
+          v[a][jj] = has_rows ? mine + xc[(a * kNB + rb + jj) * kTileN + nl] : 0.f;
+        }
 #pragma unroll
         for (int r = 0; r < R; r++) acc[a][r] = 0.f;
       }
