@@ -218,6 +218,7 @@ align_block_size_kernel(const int32_t *__restrict__ expert_ids,
 // i.e. ascending pair order (the deterministic order of the host plan), with no sort and no
 // cross-CTA scan.  Replaces two dependent launches (router_kernel + align_block_size_kernel).
 constexpr int kRouteAlignThreads = 1024;
+template <int PER>                                    // experts per lane: num_experts <= 32 * PER
 __global__ void __launch_bounds__(kRouteAlignThreads)
 route_align_small_kernel(const __half *__restrict__ logits, int32_t *__restrict__ out_ids, float *__restrict__ out_w,
                          int32_t *__restrict__ sorted_ids, int32_t *__restrict__ block_ids,
@@ -227,38 +228,48 @@ route_align_small_kernel(const __half *__restrict__ logits, int32_t *__restrict_
   extern __shared__ float s_probs[];                  // [32 warps][num_experts]
   __shared__ unsigned s_mask[kMaxExperts];            // tokens that selected expert e
   __shared__ int s_off[kMaxExperts + 1];              // padded start of expert e's run
+  __shared__ int s_ids[32 * 32];                      // expert of pair (row, k) at [row * 32 + k]
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (blockIdx.x > 0) {
     // act-order expert stack: CTA r + 1 gathers row r of the activations into sorted-k order while CTA 0 routes
     // (reference: gather_columns.cu:15 -- a separate launch in front of every grouped GEMM)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int r = blockIdx.x - 1;
-    for (int j = threadIdx.x; j < hidden; j += kRouteAlignThreads) xp[(size_t)r * hidden + j] = x[(size_t)r * hidden + perm[j]];
+    for (int j = threadIdx.x; j < hidden; j += (int)blockDim.x) xp[(size_t)r * hidden + j] = x[(size_t)r * hidden + perm[j]];
     return;
   }
-  for (int i = threadIdx.x; i < num_experts; i += kRouteAlignThreads) s_mask[i] = 0u;
+  const int nthr = (int)blockDim.x;
+  for (int i = threadIdx.x; i < num_experts; i += nthr) s_mask[i] = 0u;
   __syncthreads();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pairs = batch * top_k;
   if (warp < batch) {
+    // The probabilities of a row live in registers (expert i in lane i % 32, register i / 32); shared memory only
+    // serves the left-to-right sum.  Ids and weights leave through ONE store each (the earlier form rescaled the weights
+    // in global memory and re-read the ids there: two L2 round trips on the critical path of a decode layer).
     const int row = warp;
     float *probs = s_probs + (size_t)warp * num_experts;
+    float pv[PER];
     float tmax = -INFINITY;
-    for (int i = lane; i < num_experts; i += 32) {
-      float v = __half2float(logits[(size_t)row * num_experts + i]);
-      probs[i] = v;
-      tmax = v > tmax ? v : tmax;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const int i = j * 32 + lane;
+      pv[j] = i < num_experts ? __half2float(logits[(size_t)row * num_experts + i]) : -INFINITY;
+      tmax = pv[j] > tmax ? pv[j] : tmax;
     }
     for (int o = 16; o; o >>= 1) {
       float t = __shfl_xor_sync(0xffffffffu, tmax, o);
       tmax = t > tmax ? t : tmax;
     }
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      const int i = j * 32 + lane;
+      pv[j] = expf(pv[j] - tmax);
+      if (i < num_experts) probs[i] = pv[j];
+    }
     __syncwarp();
-    for (int i = lane; i < num_experts; i += 32) probs[i] = expf(probs[i] - tmax);
-    __syncwarp();
-    // left to right, as router.rs:150-155 -- from registers: four independent shared-memory loads in flight per
-    // step instead of one dependent load per add (the serial form cost 2 us of a 128-expert row)
+    // left to right, as router.rs:150-155 -- eight independent shared-memory loads in flight per step
     float sum = 0.f;
     if (lane == 0) {
       int i = 0;
@@ -273,41 +284,35 @@ route_align_small_kernel(const __half *__restrict__ logits, int32_t *__restrict_
     }
     sum = __shfl_sync(0xffffffffu, sum, 0);
     const float inv = 1.0f / sum;
-    for (int i = lane; i < num_experts; i += 32) probs[i] *= inv;
-    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < PER; j++) pv[j] = (j * 32 + lane < num_experts) ? pv[j] * inv : -INFINITY;
     float sel_sum = 0.f, my_w = 0.f;
-    for (int k = 0; k < top_k; k++) {
+    int my_id = 0;
+    for (int k = 0; k < top_k; k++) {                    // top_k <= 32 (route_align_small_supported)
       float best = -INFINITY;
       int best_i = 0x7fffffff;
-      for (int i = lane; i < num_experts; i += 32) {
-        float v = probs[i];
-        if (v > best) { best = v; best_i = i; }
-      }
+#pragma unroll
+      for (int j = 0; j < PER; j++)
+        if (pv[j] > best) { best = pv[j]; best_i = j * 32 + lane; }      // ascending i: the lowest index wins a tie
       for (int o = 16; o; o >>= 1) {
         float ov = __shfl_xor_sync(0xffffffffu, best, o);
         int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
         if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
       }
       if (best_i == 0x7fffffff) best_i = 0;
-      if (lane == 0) {
-        out_ids[(size_t)row * top_k + k] = best_i;
-        probs[best_i] = -INFINITY;
-        atomicOr(&s_mask[best_i], 1u << row);
-      }
-      if ((k & 31) == lane) my_w = best;                // lane k keeps weight k (top_k <= 32 per pass)
+#pragma unroll
+      for (int j = 0; j < PER; j++)
+        if (best_i == j * 32 + lane) pv[j] = -INFINITY;
+      if (lane == 0) atomicOr(&s_mask[best_i], 1u << row);
+      if (k == lane) { my_w = best; my_id = best_i; }    // lane k keeps pair k
       sel_sum += best;
-      __syncwarp();
-      if ((k & 31) == 31 || k == top_k - 1) {           // flush up to 32 weights
-        const int kk = (k & ~31) + lane;
-        if (kk <= k) out_w[(size_t)row * top_k + kk] = my_w;
-      }
     }
-    if (norm) {
-      __syncwarp();
-      for (int k = lane; k < top_k; k += 32) {
-        if (sel_sum > 0.f) out_w[(size_t)row * top_k + k] *= (1.0f / sel_sum);
-        else out_w[(size_t)row * top_k + k] = 1.0f / (float)top_k;
-      }
+    if (lane < top_k) {
+      float w = my_w;
+      if (norm) w = sel_sum > 0.f ? w * (1.0f / sel_sum) : 1.0f / (float)top_k;
+      out_ids[(size_t)row * top_k + lane] = my_id;
+      out_w[(size_t)row * top_k + lane] = w;
+      s_ids[row * 32 + lane] = my_id;
     }
   }
   __syncthreads();
@@ -330,15 +335,18 @@ route_align_small_kernel(const __half *__restrict__ logits, int32_t *__restrict_
     if (lane == 0) { s_off[num_experts] = carry; total_post_pad[0] = min(carry, (sorted_max / block_size) * block_size); }
   }
   __syncthreads();
+  // every slot of the padded runs is written exactly once: a pair id or the sentinel
   const int total = min(s_off[num_experts], sorted_max);
-  for (int i = threadIdx.x; i < total; i += kRouteAlignThreads) sorted_ids[i] = pairs;   // sentinel
-  for (int e = threadIdx.x; e < num_experts; e += kRouteAlignThreads)
+  for (int e = threadIdx.x; e < num_experts; e += nthr) {
+    const int cnt = __popc(s_mask[e]);
+    for (int i = s_off[e] + cnt; i < s_off[e + 1]; i++)
+      if (i < total) sorted_ids[i] = pairs;
     for (int b = s_off[e] / block_size; b < s_off[e + 1] / block_size; b++)
       if (b < sorted_max / block_size) block_ids[b] = e;
-  __syncthreads();
-  for (int pidx = threadIdx.x; pidx < pairs; pidx += kRouteAlignThreads) {
+  }
+  for (int pidx = threadIdx.x; pidx < pairs; pidx += nthr) {
     const int row = pidx / top_k;
-    const int e = out_ids[pidx];                        // written by this CTA (visible after the barrier)
+    const int e = s_ids[row * 32 + pidx % top_k];
     const int slot = s_off[e] + __popc(s_mask[e] & ((1u << row) - 1u));
     if (slot < sorted_max) sorted_ids[slot] = pidx;
   }
@@ -503,7 +511,7 @@ int launch_route_topk_softmax(const __half *logits, int32_t *ids, float *wts, in
 }
 
 bool route_align_small_supported(int batch, int num_experts, int top_k) {
-  return batch >= 1 && batch <= 32 && num_experts <= kMaxExperts && top_k <= num_experts &&
+  return batch >= 1 && batch <= 32 && num_experts <= kMaxExperts && top_k <= num_experts && top_k <= 32 &&
          (size_t)32 * num_experts * sizeof(float) <= 160 * 1024;
 }
 
@@ -512,12 +520,17 @@ int launch_route_align_small(const __half *logits, int32_t *ids, float *wts, int
                              int norm, int block_size, int sorted_max, cudaStream_t stream, const __half *x,
                              const int32_t *perm, __half *xp, int hidden) {
   const size_t smem = (size_t)32 * num_experts * sizeof(float);
-  if (smem > 48 * 1024)
-    FB2_CUDA_TRY(cudaFuncSetAttribute(route_align_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const bool gather = x && perm && xp && hidden > 0;
-  return launch_pdl(route_align_small_kernel, dim3(gather ? 1 + batch : 1), dim3(kRouteAlignThreads), smem, stream, logits,
-                    ids, wts, sorted_ids, block_ids, total_post_pad, batch, num_experts, top_k, norm, block_size,
-                    sorted_max, x, perm, xp, hidden);
+  // one warp per token; at least four warps for the alignment passes (and the act-order row gather CTAs)
+  const int threads = gather ? kRouteAlignThreads : std::max(128, 32 * batch);
+  auto go = [&](auto kernel) -> int {
+    if (smem > 48 * 1024) FB2_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return launch_pdl(kernel, dim3(gather ? 1 + batch : 1), dim3(threads), smem, stream, logits, ids, wts, sorted_ids,
+                      block_ids, total_post_pad, batch, num_experts, top_k, norm, block_size, sorted_max, x, perm, xp, hidden);
+  };
+  if (num_experts <= 128) return go(route_align_small_kernel<4>);
+  if (num_experts <= 256) return go(route_align_small_kernel<8>);
+  return go(route_align_small_kernel<kMaxExperts / 32>);
 }
 
 bool ep_route_plan_supported(int batch, int num_experts, int top_k, int world) {
