@@ -536,9 +536,10 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       const int c_first = e.c_first, c_last = e.c_last;
       // real rows of the block: a prefix (dense: m; routed: moe_align_block_size puts real ids first)
       int nv;
+      int row_id = 0;                                            // routed: lane i holds the pair id of row i of the block
       if constexpr (kRouted) {
-        const int id = lane < p.rm.block ? __ldcg(p.rm.sorted_ids + (size_t)blk * p.rm.block + lane) : p.rm.num_valid;
-        nv = __popc(__ballot_sync(0xffffffffu, id < p.rm.num_valid));
+        row_id = lane < p.rm.block ? __ldcg(p.rm.sorted_ids + (size_t)blk * p.rm.block + lane) : p.rm.num_valid;
+        nv = __popc(__ballot_sync(0xffffffffu, row_id < p.rm.num_valid));
       } else {
         nv = min(kNB, p.rm.m - blk * kNB);
       }
@@ -589,7 +590,7 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       const int nr = nv - rb;                                    // real rows among this group's: j < nr
       auto store_out = [&](int row_in_block, float v0, float v1) {
         int cr;
-        if constexpr (kRouted) cr = __ldcg(p.rm.sorted_ids + (size_t)blk * p.rm.block + row_in_block);   // C row = pair id
+        if constexpr (kRouted) cr = __shfl_sync(0xffffffffu, row_id, row_in_block);   // C row = pair id (warp-uniform call)
         else cr = blk * kNB + row_in_block;
         float o;
         if constexpr (kSilu) {
@@ -637,7 +638,7 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
               st_slots<VW>(slot_of(cta, a, vi), u);
             }
         } else {
-          constexpr int UB = 32 / (OWN * NACC) < 8 ? 32 / (OWN * NACC) : 8;   // contributors polled together (<= 32 registers)
+          constexpr int UB = 32 / (OWN * NACC) < 8 ? 32 / (OWN * NACC) : 8;   // contributors polled together (<= 32 registers: more spills)
 #pragma unroll 1
           for (int c0 = c_first + 1; c0 <= c_last; c0 += UB) {
             uint32_t t[UB][NACC][NV][VW];

@@ -1144,15 +1144,25 @@ int launch_dk_rows_silu(int m, const TcPlan &pl, cudaStream_t stream, const TcPa
          : m <= 4 ? launch_dk<4, kMode, true, false>(pl, stream, p, xmap) : launch_dk<8, kMode, true, false>(pl, stream, p, xmap);
 }
 template <int kMode, bool kPush>
+int launch_dk32(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
+  if constexpr (kMode == dk::DK_DENSE && !kPush) {
+    return launch_dk<32, kMode, false, kPush>(pl, stream, p, xmap);
+  } else {
+    set_error("internal: the 32-row decode kernel serves plain dense launches only");
+    return FB2_ERR_ARG;
+  }
+}
+template <int kMode, bool kPush>
 int launch_dk_rows(int m, const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
   return m <= 1 ? launch_dk<1, kMode, false, kPush>(pl, stream, p, xmap)
          : m <= 2 ? launch_dk<2, kMode, false, kPush>(pl, stream, p, xmap)
          : m <= 4 ? launch_dk<4, kMode, false, kPush>(pl, stream, p, xmap)
          : m <= 8 ? launch_dk<8, kMode, false, kPush>(pl, stream, p, xmap)
-         : launch_dk<16, kMode, false, kPush>(pl, stream, p, xmap);
-  // (a 32-row instantiation exists in tc_decode.cuh -- R = 32, UMMA N = 32 -- and was measured: 16.6 / 16.2 / 29.4 /
-  // 23.8 us on the four Llama shapes at M = 32 against 13.5 / 13.1 / 23.9 / 21.4 us of tc_body<32>: 32 running sums per
-  // thread spill, and the per-unit accumulator read-out grows with the rows.  Not instantiated.)
+         : m <= 16 ? launch_dk<16, kMode, false, kPush>(pl, stream, p, xmap)
+         : launch_dk32<kMode, kPush>(pl, stream, p, xmap);
+  // (17..32 rows: R = 32, UMMA N = 32.  With 80 registers per thread its 32 running sums spilled and it lost to
+  // tc_body<32>; with the dequant warpgroups at 96 registers it wins: 9.97 / 9.41 / 20.5 / 15.9 us on the four Llama
+  // shapes at M = 32 against 11.8 / 11.2 / 22.8 / 17.7 us.)
 }
 
 template <int NB>
@@ -1168,12 +1178,12 @@ int launch_dispatch(const TcPlan &pl, cudaStream_t stream, const TcParams &p, co
 
 }  // namespace
 
-// The decode kernel (tc_decode.cuh) serves dense launches of at most 16 rows (8 with the SwiGLU epilogue: two
+// The decode kernel (tc_decode.cuh) serves dense launches of at most 32 rows (8 with the SwiGLU epilogue: two
 // accumulators' worth of running sums per thread).
 static bool dk_eligible(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue) {
   static const bool no_dk = [] { const char *e = getenv("FB2_DEBUG_NO_DK"); return e && e[0] == '1'; }();
-  static const int max_m = [] { const char *e = getenv("FB2_DEBUG_DK_MAXM"); return e ? atoi(e) : 16; }();
-  return !no_dk && rows.mode == ROWS_DENSE && rows.m >= 1 && rows.m <= max_m && rows.m <= (epilogue ? 8 : 16) && !tbl;
+  static const int max_m = [] { const char *e = getenv("FB2_DEBUG_DK_MAXM"); return e ? atoi(e) : 32; }();
+  return !no_dk && rows.mode == ROWS_DENSE && rows.m >= 1 && rows.m <= max_m && rows.m <= (epilogue ? 8 : 32) && !tbl;
 }
 // ... and gathers act-order activations itself when the m rows of x fit next to a weight ring of kMinWStages
 bool dk_gather_ok(const WeightRef &w, const RowMap &rows, const DispatchTable *tbl, int epilogue) {
