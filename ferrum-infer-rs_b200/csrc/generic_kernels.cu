@@ -216,10 +216,10 @@ __global__ void permute_cols_kernel(const __half *__restrict__ x, const int32_t 
   // PDL: let the GEMM that follows start streaming its weights now; wait for the previous GEMM
   // (which may still be reading the shared xp scratch) before writing.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int src = j < k ? perm[j] : 0;            // a weight-side constant: in flight before the grid dependency resolves
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (j >= k) return;
-  const int src = perm[j];
   for (int r = blockIdx.y; r < m; r += gridDim.y) xp[(size_t)r * k + j] = x[(size_t)r * k + src];
 }
 

@@ -40,15 +40,17 @@ constexpr int kWarpMma2 = 11;               // second MMA issuer: one per dequan
                                             // one in-order issue loop (the 12th warp costs no registers: 11 warps already
                                             // occupy the allocation of 12)
 constexpr int kDkThreads = 12 * 32;
-constexpr int kXSlots = 4;
+constexpr int kXSlots = 4;                  // activation ring: slots of a dense launch ...
+constexpr int kXSlotsRouted = 8;            // ... and of a routed one (its gathers are L2 round trips per unit: the down projection
+                                            // of a MoE layer waited for activations a third of the time with four)
 constexpr int kSmemBudget = 108 * 1024;     // two CTAs per SM
 // shared memory: [X slots][group exchange][barriers + misc][weight ring: run-time depth][DK_GATHER: the x rows]
 // NB = UMMA N = rows of a block: 16, or 32 for the 17..32-row dense launches
-template <bool kSilu, int NB>
+template <bool kSilu, int NB, int SX = kXSlots>
 struct Lay {
   static constexpr int kNacc = kSilu ? 2 : 1;
   static constexpr int kXBytes = NB * 256;                       // [2 atoms][NB rows][128 B]
-  static constexpr int kXchgBase = kXSlots * kXBytes;
+  static constexpr int kXchgBase = SX * kXBytes;
   static constexpr int kXchgBytes = kNacc * NB * kTileN * 4;     // group <-> group exchange of partial sums
   static constexpr int kBarBase = kXchgBase + kXchgBytes;
   static constexpr int kWBase = kBarBase + 1024;
@@ -64,8 +66,8 @@ static_assert(w_stages_for(true, 0) >= 7 && w_stages_for(false, 0, 32) >= 6, "we
 constexpr int kTmemCols = 256;
 constexpr int kColA = 0;                    // 2 slots x 64
 constexpr int kColD = 128;                  // 2 x NB: 2^-24 * sum_k (q_k - z) x_k; behind it 2 x 8 columns of half2(-z, -z) * 2^-24
-enum { BAR_FULL_W = 0, BAR_EMPTY_W = kMaxWStages, BAR_FULL_X = 2 * kMaxWStages, BAR_EMPTY_X = BAR_FULL_X + kXSlots,
-       BAR_FULL_A = BAR_EMPTY_X + kXSlots, BAR_DONE = BAR_FULL_A + 2, BAR_XS = BAR_DONE + 2, BAR_COUNT = BAR_XS + 1 };
+enum { BAR_FULL_W = 0, BAR_EMPTY_W = kMaxWStages, BAR_FULL_X = 2 * kMaxWStages, BAR_EMPTY_X = BAR_FULL_X + kXSlotsRouted,
+       BAR_FULL_A = BAR_EMPTY_X + kXSlotsRouted, BAR_DONE = BAR_FULL_A + 2, BAR_XS = BAR_DONE + 2, BAR_COUNT = BAR_XS + 1 };
 static_assert(BAR_COUNT * 8 <= 512, "barrier area too small");
 // TcParams::dk_flags
 enum { DKF_META_EARLY = 1,      // routed: the routing arrays were complete before the PREVIOUS kernel started its
@@ -157,10 +159,10 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
   constexpr int kColZ = kColD + 2 * kNB;
   static_assert(kColZ + 16 <= kTmemCols, "tensor memory map");
   static_assert(!(kSilu && kPush) && !(kPush && kMode == DK_ROUTED) && !(kSilu && R > 8), "combination not instantiated");
-  using L = Lay<kSilu, kNB>;
+  constexpr int SX = kMode == DK_ROUTED ? kXSlotsRouted : kXSlots;
+  using L = Lay<kSilu, kNB, SX>;
   constexpr int kXBytes = L::kXBytes;
   constexpr int NACC = L::kNacc;
-  constexpr int SX = kXSlots;
   constexpr bool kRouted = kMode == DK_ROUTED, kGather = kMode == DK_GATHER;
   constexpr int OWN = R <= 4 ? R : R / 2;           // rows a group finishes in the epilogue (group 1: none when R <= 4)
   constexpr int kEpiThreads = R <= 4 ? 128 : 256;   // threads that take part in the inter-CTA exchange
@@ -400,10 +402,10 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
     const uint32_t s = warp == kWarpMma2 ? 1u : 0u;
     const uint32_t a = tmem_base + kColA + s * 64;
     const uint32_t d = tmem_base + kColD + s * kNB, zc = tmem_base + kColZ + s * 8;
-    static_assert(SX == 4, "activation ring position is computed from the unit index");
+    static_assert(SX == 4 || SX == 8, "activation ring position is computed from the unit index");
 #pragma unroll 1
     for (u32 li = s; li < n_units; li += 2) {
-      const uint32_t xst = li & 3u, xpar = (li >> 2) & 1u;
+      const uint32_t xst = li & (u32)(SX - 1), xpar = (li / (u32)SX) & 1u;
       ptx::mbar_wait(bar(BAR_FULL_X + xst), xpar);                // activation slice landed
       if (kRouted) ptx::fence_proxy_async_smem();                 // cp.async rows were generic-proxy writes
       if (li == 0) FB2_TLW(13);

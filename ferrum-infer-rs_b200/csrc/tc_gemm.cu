@@ -1369,7 +1369,7 @@ int launch_tc_gemm(const WeightRef &w, const RowMap &rows, const DispatchTable *
     p.fd_units = make_fastdiv((u32)pl.units);
     const bool pushing = push && push->world;
     if (use_dk_routed) {
-      p.w_stages = dk::w_stages_for(epilogue != 0, 0);
+      p.w_stages = dk::w_stages_for(epilogue != 0, (dk::kXSlotsRouted - dk::kXSlots) * dk::Lay<false, 16>::kXBytes);
       if (rows.block <= 8) {
         rc = epilogue ? launch_dk<8, dk::DK_ROUTED, true, false>(pl, stream, p, xmap)
                       : launch_dk<8, dk::DK_ROUTED, false, false>(pl, stream, p, xmap);
