@@ -184,7 +184,11 @@ struct TcScratch {
   uint32_t *ll;                      // flag-in-value partial slots of small-batch split tiles (tc_gemm.cu)
   int ll_ctas;                       // CTAs the area serves; 0 = exchange disabled
 };
-constexpr int kLlMaxCtas = 1024;                 // >= 2 CTAs per SM on any sm_100 part
+#ifndef FB2_LL_MAX_CTAS
+#define FB2_LL_MAX_CTAS 1536
+#endif
+constexpr int kLlMaxCtas = FB2_LL_MAX_CTAS;                 // tc_body: one area per CTA; the decode kernel: up to four.  (NOT 2048: a 16 MB area
+                                                 // shifted the weight allocations behind it so that the widest decode GEMM lost 2.4 us: measured, cause not pinned down)
 constexpr size_t kLlBytes = (size_t)kLlMaxCtas * 2 * 8 * 128 * sizeof(uint32_t);   // [ctas][2 acc][8 rows][128]
 bool tc_supported(const WeightRef &w);
 // act-order launches the decode kernel gathers itself (no permute launch, w.perm stays set)

@@ -588,7 +588,12 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
       const bool owner = !whole && cta == c_first;
       // flag-in-value exchange: the slot area of a CTA, [2 accumulators][8 rows][128], holds either pair of 8-row
       // accumulators or the 16 rows of one
-      const bool ll = !whole && NACC * R <= 16 && G <= p.ll_ctas;   // (R = 32: partial tiles + counter)
+      // 16+ rows: distributed owners (below); fewer: the first contributor finishes the tile alone -- as fast while one
+      // polling round covers every contributor, and the others leave their SM slots to the next launch earlier
+      constexpr bool kDist = R >= 16;
+      constexpr int kAreaFloats = NACC * R * kTileN;             // kDist: one slot area, [acc][R rows][128]; a CTA has two
+      static_assert(!kDist || kAreaFloats % kLlFloatsPerCta == 0, "slot areas are whole tc_body areas");
+      const bool ll = !whole && (kDist ? G * 2 * (kAreaFloats / kLlFloatsPerCta) <= p.ll_ctas : G <= p.ll_ctas);
       const int nr = nv - rb;                                    // real rows among this group's: j < nr
       auto store_out = [&](int row_in_block, float v0, float v1) {
         int cr;
@@ -613,105 +618,277 @@ __device__ __forceinline__ void dk_body(const TcParams &p, const CUtensorMap *xm
         for (int jj = 0; jj < OWN; jj++)
           if (jj < nr) store_out(rb + jj, v[0][jj], v[NACC - 1][jj]);
       } else if (ll) {
-        // ---- flag-in-value exchange (protocol: tc_gemm.cu).  Slot layout of this kernel: [cta][acc][16 / VW][column][VW],
-        // so the OWN rows of a thread are ONE vector store for the contributor and one vector load per contributor
-        // for the owner.  Rows >= nv carry whatever the accumulator columns held: they are published, summed and
-        // reset like real ones (never stored to y), which keeps the vectors whole.
-#ifdef FB2_LL_SCALAR
-        constexpr int VW = 1;
-#else
-        constexpr int VW = OWN < 4 ? OWN : 4;                    // vector width
-#endif
-        constexpr int NV = OWN / VW;                             // vectors per thread, accumulator and contributor
-        auto slot_of = [&](int c, int a, int vi) {
-          return p.ll + (size_t)c * kLlFloatsPerCta + (size_t)(((a * R + rb) / VW + vi) * kTileN + nl) * VW;
-        };
-        if (!owner) {
-#pragma unroll
-          for (int a = 0; a < NACC; a++)
-#pragma unroll
-            for (int vi = 0; vi < NV; vi++) {
+        if constexpr (kDist) {
+          // ---- flag-in-value exchange (protocol: tc_gemm.cu) with DISTRIBUTED owners.  Slot layout of this kernel:
+          // [cta][acc][R / VW row vectors][column][VW].  The rows of a split tile are finished in vectors of VW rows, and
+          // vector rv belongs to contributor c_first + rv % (n - 1): every contributor publishes the vectors it does not
+          // own (one vector store each) and sums the ones it owns from all the others -- ONE batch of loads per owned
+          // vector instead of the single owner's several (a tile of a small layer is cut 6..10 ways, and with 8 or 16 rows
+          // the owner's register budget allowed four contributors per polling round).  The last contributor owns
+          // nothing: the tile is the FIRST segment of its range, and waiting there would chain the CTAs one behind the
+          // other; for every other contributor the tile is the last thing it does.  Rows >= nv carry whatever the
+          // accumulator columns held: they are published, summed and reset like real ones (never stored to y).
+          constexpr int VB = OWN < 4 ? OWN : 4;
+          constexpr int VW = VB / NACC > 0 ? VB / NACC : 1;        // rows per vector (the SwiGLU pair moves two accumulators)
+          constexpr int NV = OWN / VW;                             // row vectors per thread
+          constexpr int UB = 32 / (NACC * VW) < 8 ? 32 / (NACC * VW) : 8;   // contributors polled together (<= 32 registers)
+          const int n_own = c_last - c_first >= 3 ? c_last - c_first : 1;   // four or more contributors: all but the last own
+          const int me = cta - c_first;
+          // A CTA contributes to at most two split tiles -- the one its range starts in (it is that tile's last
+          // contributor) and the one it ends in -- and has one slot area for each.
+          auto slot_of = [&](int c, int a, int vi) {
+            return p.ll + ((size_t)c * 2 + (c == c_last ? 0 : 1)) * kAreaFloats +
+                   (size_t)(((a * R + rb) / VW + vi) * kTileN + nl) * VW;
+          };
+  #pragma unroll
+          for (int vi = 0; vi < NV; vi++) {
+            if ((rb / VW + vi) % n_own == me) continue;            // mine to finish (group-uniform)
+  #pragma unroll
+            for (int a = 0; a < NACC; a++) {
               uint32_t u[VW];
-#pragma unroll
+  #pragma unroll
               for (int ee = 0; ee < VW; ee++) {
                 u[ee] = __float_as_uint(v[a][vi * VW + ee]);
                 if (u[ee] == kLlEmpty) u[ee] = 0x7fffffffu;
               }
               st_slots<VW>(slot_of(cta, a, vi), u);
             }
-        } else {
-          constexpr int UB = 32 / (OWN * NACC) < 8 ? 32 / (OWN * NACC) : 8;   // contributors polled together (<= 32 registers: more spills)
-#pragma unroll 1
-          for (int c0 = c_first + 1; c0 <= c_last; c0 += UB) {
-            uint32_t t[UB][NACC][NV][VW];
+          }
+            if (n_own == 1) {
+            // two or three contributors (the wide layers: a tile is cut once or twice): the first one takes every vector of
+            // the others in ONE polling round -- vector by vector it would pay a round trip per owned vector, and the
+            // others would hold their SM slots for nothing
+            if (me == 0) {
+              constexpr int UJ = 2;
+              uint32_t t[UJ][NACC][NV][VW];
 #pragma unroll
-            for (int i = 0; i < UB; i++)
-#pragma unroll
-              for (int a = 0; a < NACC; a++)
-#pragma unroll
-                for (int vi = 0; vi < NV; vi++) {
-                  if (c0 + i <= c_last) {
-                    ld_slots<VW>(slot_of(c0 + i, a, vi), t[i][a][vi]);
-                  } else {
-#pragma unroll
-                    for (int ee = 0; ee < VW; ee++) t[i][a][vi][ee] = 0u;
-                  }
-                }
-#ifdef FB2_WAIT_TIMEOUT
-            const long long t0 = clock64();
-#endif
-#ifdef FB2_TRACE
-            int rounds = 0;
-#endif
-            for (;;) {
-              // all slots are tested first and all missing vectors re-requested together
-              bool waiting = false;
-#pragma unroll
-              for (int i = 0; i < UB; i++)
-#pragma unroll
-                for (int a = 0; a < NACC; a++)
-#pragma unroll
-                  for (int vi = 0; vi < NV; vi++)
-#pragma unroll
-                    for (int ee = 0; ee < VW; ee++) waiting |= t[i][a][vi][ee] == kLlEmpty;
-              if (!waiting) break;
-#ifdef FB2_TRACE
-              rounds++;
-#endif
-#pragma unroll
-              for (int i = 0; i < UB; i++)
+              for (int i = 0; i < UJ; i++)
 #pragma unroll
                 for (int a = 0; a < NACC; a++)
 #pragma unroll
                   for (int vi = 0; vi < NV; vi++) {
-                    bool miss = false;
+                    if (c_first + 1 + i <= c_last) {
+                      ld_slots<VW>(slot_of(c_first + 1 + i, a, vi), t[i][a][vi]);
+                    } else {
 #pragma unroll
-                    for (int ee = 0; ee < VW; ee++) miss |= t[i][a][vi][ee] == kLlEmpty;
-                    if (miss) ld_slots<VW>(slot_of(c0 + i, a, vi), t[i][a][vi]);   // only ever true for vectors that were requested
+                      for (int ee = 0; ee < VW; ee++) t[i][a][vi][ee] = 0u;
+                    }
                   }
 #ifdef FB2_WAIT_TIMEOUT
-              if (clock64() - t0 > 4000000000LL) { printf("fb2: ll slot wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
+              const long long t0 = clock64();
 #endif
+              for (;;) {
+                bool waiting = false;
+#pragma unroll
+                for (int i = 0; i < UJ; i++)
+#pragma unroll
+                  for (int a = 0; a < NACC; a++)
+#pragma unroll
+                    for (int vi = 0; vi < NV; vi++)
+#pragma unroll
+                      for (int ee = 0; ee < VW; ee++) waiting |= t[i][a][vi][ee] == kLlEmpty;
+                if (!waiting) break;
+#pragma unroll
+                for (int i = 0; i < UJ; i++)
+#pragma unroll
+                  for (int a = 0; a < NACC; a++)
+#pragma unroll
+                    for (int vi = 0; vi < NV; vi++) {
+                      bool miss = false;
+#pragma unroll
+                      for (int ee = 0; ee < VW; ee++) miss |= t[i][a][vi][ee] == kLlEmpty;
+                      if (miss) ld_slots<VW>(slot_of(c_first + 1 + i, a, vi), t[i][a][vi]);
+                    }
+#ifdef FB2_WAIT_TIMEOUT
+                if (clock64() - t0 > 4000000000LL) { printf("fb2: ll slot wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
+#endif
+              }
+              FB2_TL(9);
+#pragma unroll
+              for (int i = 0; i < UJ; i++)
+#pragma unroll
+                for (int a = 0; a < NACC; a++)
+#pragma unroll
+                  for (int vi = 0; vi < NV; vi++)
+                    if (c_first + 1 + i <= c_last) {
+#pragma unroll
+                      for (int ee = 0; ee < VW; ee++) v[a][vi * VW + ee] += __uint_as_float(t[i][a][vi][ee]);
+                      reset_slots<VW>(slot_of(c_first + 1 + i, a, vi));
+                    }
+#pragma unroll
+              for (int jj = 0; jj < OWN; jj++)
+                if (jj < nr) store_out(rb + jj, v[0][jj], v[NACC - 1][jj]);
             }
-            FB2_TL(9);
-#ifdef FB2_TRACE
-            FB2_TLV(15, rounds);
-#endif
+          } else {
 #pragma unroll
-            for (int i = 0; i < UB; i++)
-#pragma unroll
-              for (int a = 0; a < NACC; a++)
-#pragma unroll
-                for (int vi = 0; vi < NV; vi++)
-                  if (c0 + i <= c_last) {
-#pragma unroll
-                    for (int ee = 0; ee < VW; ee++) v[a][vi * VW + ee] += __uint_as_float(t[i][a][vi][ee]);
+          for (int vi = 0; vi < NV; vi++) {
+            if ((rb / VW + vi) % n_own != me) continue;
+  #pragma unroll 1
+            for (int c0 = c_first; c0 <= c_last; c0 += UB) {
+              uint32_t t[UB][NACC][VW];
+  #pragma unroll
+              for (int i = 0; i < UB; i++)
+  #pragma unroll
+                for (int a = 0; a < NACC; a++) {
+                  if (c0 + i <= c_last && c0 + i != cta) {
+                    ld_slots<VW>(slot_of(c0 + i, a, vi), t[i][a]);
+                  } else {
+  #pragma unroll
+                    for (int ee = 0; ee < VW; ee++) t[i][a][ee] = 0u;
+                  }
+                }
+  #ifdef FB2_WAIT_TIMEOUT
+              const long long t0 = clock64();
+  #endif
+  #ifdef FB2_TRACE
+              int rounds = 0;
+  #endif
+              for (;;) {
+                // all slots are tested first and all missing vectors re-requested together
+                bool waiting = false;
+  #pragma unroll
+                for (int i = 0; i < UB; i++)
+  #pragma unroll
+                  for (int a = 0; a < NACC; a++)
+  #pragma unroll
+                    for (int ee = 0; ee < VW; ee++) waiting |= t[i][a][ee] == kLlEmpty;
+                if (!waiting) break;
+  #ifdef FB2_TRACE
+                rounds++;
+  #endif
+  #pragma unroll
+                for (int i = 0; i < UB; i++)
+  #pragma unroll
+                  for (int a = 0; a < NACC; a++) {
+                    bool miss = false;
+  #pragma unroll
+                    for (int ee = 0; ee < VW; ee++) miss |= t[i][a][ee] == kLlEmpty;
+                    if (miss) ld_slots<VW>(slot_of(c0 + i, a, vi), t[i][a]);   // only ever true for vectors that were requested
+                  }
+  #ifdef FB2_WAIT_TIMEOUT
+                if (clock64() - t0 > 4000000000LL) { printf("fb2: ll slot wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
+  #endif
+              }
+              FB2_TL(9);
+  #ifdef FB2_TRACE
+              FB2_TLV(15, rounds);
+  #endif
+  #pragma unroll
+              for (int i = 0; i < UB; i++)
+  #pragma unroll
+                for (int a = 0; a < NACC; a++)
+                  if (c0 + i <= c_last && c0 + i != cta) {
+  #pragma unroll
+                    for (int ee = 0; ee < VW; ee++) v[a][vi * VW + ee] += __uint_as_float(t[i][a][ee]);
                     reset_slots<VW>(slot_of(c0 + i, a, vi));         // consumed: empty again for the next launch
                   }
+            }
+  #pragma unroll
+            for (int ee = 0; ee < VW; ee++)
+              if (vi * VW + ee < nr) store_out(rb + vi * VW + ee, v[0][vi * VW + ee], v[NACC - 1][vi * VW + ee]);
           }
-#pragma unroll
-          for (int jj = 0; jj < OWN; jj++)
-            if (jj < nr) store_out(rb + jj, v[0][jj], v[NACC - 1][jj]);
+          }
+        } else {
+          // ---- flag-in-value exchange (protocol: tc_gemm.cu).  Slot layout of this kernel: [cta][acc][16 / VW][column][VW],
+          // so the OWN rows of a thread are ONE vector store for the contributor and one vector load per contributor
+          // for the owner.  Rows >= nv carry whatever the accumulator columns held: they are published, summed and
+          // reset like real ones (never stored to y), which keeps the vectors whole.
+  #ifdef FB2_LL_SCALAR
+          constexpr int VW = 1;
+  #else
+          constexpr int VW = OWN < 4 ? OWN : 4;                    // vector width
+  #endif
+          constexpr int NV = OWN / VW;                             // vectors per thread, accumulator and contributor
+          auto slot_of = [&](int c, int a, int vi) {
+            return p.ll + (size_t)c * kLlFloatsPerCta + (size_t)(((a * R + rb) / VW + vi) * kTileN + nl) * VW;
+          };
+          if (!owner) {
+  #pragma unroll
+            for (int a = 0; a < NACC; a++)
+  #pragma unroll
+              for (int vi = 0; vi < NV; vi++) {
+                uint32_t u[VW];
+  #pragma unroll
+                for (int ee = 0; ee < VW; ee++) {
+                  u[ee] = __float_as_uint(v[a][vi * VW + ee]);
+                  if (u[ee] == kLlEmpty) u[ee] = 0x7fffffffu;
+                }
+                st_slots<VW>(slot_of(cta, a, vi), u);
+              }
+          } else {
+            constexpr int UB = 32 / (OWN * NACC) < 8 ? 32 / (OWN * NACC) : 8;   // contributors polled together (<= 32 registers: more spills)
+  #pragma unroll 1
+            for (int c0 = c_first + 1; c0 <= c_last; c0 += UB) {
+              uint32_t t[UB][NACC][NV][VW];
+  #pragma unroll
+              for (int i = 0; i < UB; i++)
+  #pragma unroll
+                for (int a = 0; a < NACC; a++)
+  #pragma unroll
+                  for (int vi = 0; vi < NV; vi++) {
+                    if (c0 + i <= c_last) {
+                      ld_slots<VW>(slot_of(c0 + i, a, vi), t[i][a][vi]);
+                    } else {
+  #pragma unroll
+                      for (int ee = 0; ee < VW; ee++) t[i][a][vi][ee] = 0u;
+                    }
+                  }
+  #ifdef FB2_WAIT_TIMEOUT
+              const long long t0 = clock64();
+  #endif
+  #ifdef FB2_TRACE
+              int rounds = 0;
+  #endif
+              for (;;) {
+                // all slots are tested first and all missing vectors re-requested together
+                bool waiting = false;
+  #pragma unroll
+                for (int i = 0; i < UB; i++)
+  #pragma unroll
+                  for (int a = 0; a < NACC; a++)
+  #pragma unroll
+                    for (int vi = 0; vi < NV; vi++)
+  #pragma unroll
+                      for (int ee = 0; ee < VW; ee++) waiting |= t[i][a][vi][ee] == kLlEmpty;
+                if (!waiting) break;
+  #ifdef FB2_TRACE
+                rounds++;
+  #endif
+  #pragma unroll
+                for (int i = 0; i < UB; i++)
+  #pragma unroll
+                  for (int a = 0; a < NACC; a++)
+  #pragma unroll
+                    for (int vi = 0; vi < NV; vi++) {
+                      bool miss = false;
+  #pragma unroll
+                      for (int ee = 0; ee < VW; ee++) miss |= t[i][a][vi][ee] == kLlEmpty;
+                      if (miss) ld_slots<VW>(slot_of(c0 + i, a, vi), t[i][a][vi]);   // only ever true for vectors that were requested
+                    }
+  #ifdef FB2_WAIT_TIMEOUT
+                if (clock64() - t0 > 4000000000LL) { printf("fb2: ll slot wait timed out (cta %d tile %d)\n", cta, tau); __trap(); }
+  #endif
+              }
+              FB2_TL(9);
+  #ifdef FB2_TRACE
+              FB2_TLV(15, rounds);
+  #endif
+  #pragma unroll
+              for (int i = 0; i < UB; i++)
+  #pragma unroll
+                for (int a = 0; a < NACC; a++)
+  #pragma unroll
+                  for (int vi = 0; vi < NV; vi++)
+                    if (c0 + i <= c_last) {
+  #pragma unroll
+                      for (int ee = 0; ee < VW; ee++) v[a][vi * VW + ee] += __uint_as_float(t[i][a][vi][ee]);
+                      reset_slots<VW>(slot_of(c0 + i, a, vi));         // consumed: empty again for the next launch
+                    }
+            }
+  #pragma unroll
+            for (int jj = 0; jj < OWN; jj++)
+              if (jj < nr) store_out(rb + jj, v[0][jj], v[NACC - 1][jj]);
+          }
         }
       } else {
         // ---- counter exchange: partial tile + self-resetting arrival counter
