@@ -413,7 +413,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": pk["src"],
-                         "kernel": "dk_gemm_kernel (M <= 16) / tc_gemm_kernel (M = 32): stream-K, tcgen05",
+                         "kernel": "dk_gemm_kernel (decode kernel, M <= 32): stream-K, tcgen05",
                          "avg_launch_us": round(avg_launch_us, 3),
                          "alg_bytes_per_launch": int(step_bytes / n_gemms)},
             "cpu_baseline": cpu, "series_decode": series, "per_shape_M1": per_shape, "prefill": prefill,

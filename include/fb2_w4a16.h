@@ -95,7 +95,7 @@ FB2_API size_t fb2_gptq_linear_out_features(const fb2_linear_t *lin);
 /* 1 when the layer was loaded with a non-trivial g_idx (quant.rs:685-711). */
 FB2_API int fb2_gptq_linear_is_act_order(const fb2_linear_t *lin);
 /* Name of the kernel family forward() will use for `m` rows ("tc-streamk": the tensor-core kernels of up to 64-row
- * blocks -- the decode kernel of csrc/tc_decode.cuh up to 16 rows; "tc-streamk-prefill": 128 / 256-row blocks;
+ * blocks -- the decode kernel of csrc/tc_decode.cuh up to 32 rows; "tc-streamk-prefill": 128 / 256-row blocks;
  * "generic": shapes outside the tile format): introspection for tests and the bench, not a dispatch knob. */
 FB2_API const char *fb2_gptq_linear_kernel_name(const fb2_linear_t *lin, size_t m);
 
