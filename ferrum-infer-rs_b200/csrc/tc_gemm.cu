@@ -1145,10 +1145,10 @@ int launch_dk_rows_silu(int m, const TcPlan &pl, cudaStream_t stream, const TcPa
 }
 template <int kMode, bool kPush>
 int launch_dk32(const TcPlan &pl, cudaStream_t stream, const TcParams &p, const CUtensorMap &xmap) {
-  if constexpr (kMode == dk::DK_DENSE && !kPush) {
+  if constexpr (kMode == dk::DK_DENSE) {
     return launch_dk<32, kMode, false, kPush>(pl, stream, p, xmap);
   } else {
-    set_error("internal: the 32-row decode kernel serves plain dense launches only");
+    set_error("internal: the 32-row decode kernel takes its rows through the tensor map only");
     return FB2_ERR_ARG;
   }
 }
