@@ -61,6 +61,7 @@ SIGNATURES = {
     "fb2_gptq_linear_forward": (_i32, [_vp, _vp, _vp, _vp, _sz]),
     "fb2_gptq_linear_forward_host": (_i32, [_vp, _vp, _vp, _sz]),
     "fb2_gptq_linear_forward_host_batch": (_i32, [_vp, _sz, _vp, _vp, _sz]),
+    "fb2_gptq_linear_forward_host_batch_m": (_i32, [_vp, _sz, _vp, _vp, _vp]),
     "fb2_gptq_linear_dequant_f32": (_i32, [_vp, _vp, _vp]),
     "fb2_gptq_linear_dequant_f16": (_i32, [_vp, _vp, _vp]),
     "fb2_gemm_algorithmic_bytes": (_u64, [_sz, _sz, _sz, _sz, _i32]),

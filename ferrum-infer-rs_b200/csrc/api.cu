@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <numeric>
 #include <vector>
@@ -280,6 +281,10 @@ struct fb2_linear {
   size_t stage_rows = 0;
   cudaStream_t host_stream = nullptr;
 };
+
+// Bumped whenever a linear is created or destroyed: invalidates the launch graphs cached by the host-buffer batch call
+// (a new handle may reuse a destroyed one's address).
+static std::atomic<uint64_t> g_handle_gen{1};
 
 static void free_all(std::vector<void *> &v) {
   for (void *p : v)
@@ -550,6 +555,7 @@ int fb2_gptq_linear_create(const int32_t *qweight, const float *scales, const in
   }
   if ((rc = reserve_scratch_for(w, device, 64))) return fail(rc);
   registry_add(lin, device, w);
+  g_handle_gen.fetch_add(1);
   *out = lin;
   return FB2_OK;
 }
@@ -558,6 +564,7 @@ void fb2_gptq_linear_destroy(fb2_linear_t *lin) {
   if (!lin) return;
   cudaSetDevice(lin->device);
   registry_remove(lin);
+  g_handle_gen.fetch_add(1);
   free_all(lin->allocs);
   if (lin->h_x) cudaFreeHost(lin->h_x);
   if (lin->h_y) cudaFreeHost(lin->h_y);
@@ -724,28 +731,55 @@ int fb2_gptq_linear_forward_host(fb2_linear_t *lin, const fb2_half *x_host, fb2_
 }
 
 // One pinned + one device arena per device for the host-buffer batch call.
+// The GEMM launches of one chunk, captured once per (linears, m) and replayed: a repeated batch call (a decode loop) pays one
+// graph launch per chunk instead of per-GEMM launch, tensor-map and attribute calls, and gets the kernels' programmatic
+// dependent launch edges.  Keyed by the handle list, m, the arena base and the handle generation.
+struct BatchGraphs {
+  std::vector<const fb2_linear_t *> lins;
+  std::vector<size_t> ms;
+  uint64_t gen = 0;
+  const uint8_t *base = nullptr;
+  bool no_graph = false;                       // capture failed once: stay on the eager path
+  std::vector<cudaGraphExec_t> chunk;          // empty until the second call with this key
+  std::vector<int> chunk_launches;             // kernels in each chunk's graph (fb2_launch_count bookkeeping)
+  uint64_t last_use = 0;
+};
 struct HostArena {
   std::mutex mu;
   uint8_t *h = nullptr, *d = nullptr;
   size_t bytes = 0;
   cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
+  std::vector<BatchGraphs> graphs;
+  uint64_t tick = 0;
 };
+static void drop_graphs(BatchGraphs &g) {
+  for (cudaGraphExec_t e : g.chunk)
+    if (e) cudaGraphExecDestroy(e);
+  g.chunk.clear();
+}
 static HostArena g_arena[kMaxDevices];
 static std::mutex &host_call_mutex(int device) { return g_arena[device < 0 || device >= kMaxDevices ? 0 : device].mu; }
 
-int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
-                                       const fb2_half *const *x_host, fb2_half *const *y_host,
-                                       size_t m) {
-  if (n == 0 || m == 0) return FB2_OK;
-  if (!lins || !x_host || !y_host) { set_error("NULL argument"); return FB2_ERR_ARG; }
+// Entry i has ms[i] rows (entries with zero rows are skipped).
+int fb2_gptq_linear_forward_host_batch_m(fb2_linear_t *const *lins, size_t n,
+                                         const fb2_half *const *x_host, fb2_half *const *y_host,
+                                         const size_t *ms) {
+  if (n == 0) return FB2_OK;
+  if (!lins || !x_host || !y_host || !ms) { set_error("NULL argument"); return FB2_ERR_ARG; }
+  size_t max_m = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (ms[i] > (size_t)INT32_MAX / 2) { set_error("m too large"); return FB2_ERR_SHAPE; }
+    max_m = std::max(max_m, ms[i]);
+  }
+  if (max_m == 0) return FB2_OK;
   const int device = lins[0] ? lins[0]->device : -1;
   size_t in_bytes = 0, out_bytes = 0;
   for (size_t i = 0; i < n; i++) {
     if (!lins[i] || !x_host[i] || !y_host[i]) { set_error("NULL entry %zu", i); return FB2_ERR_ARG; }
     if (lins[i]->device != device) { set_error("all linears of a batch call must share a device"); return FB2_ERR_ARG; }
-    in_bytes += align256(m * lins[i]->w.k * 2);
-    out_bytes += align256(m * lins[i]->w.n * 2);
+    in_bytes += align256(ms[i] * lins[i]->w.k * 2);
+    out_bytes += align256(ms[i] * lins[i]->w.n * 2);
   }
   FB2_CUDA_TRY(cudaSetDevice(device));
   HostArena &A = g_arena[device];
@@ -756,11 +790,13 @@ int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
     if (A.d) cudaFree(A.d);
     A.h = A.d = nullptr;
     A.bytes = 0;
+    for (BatchGraphs &g : A.graphs) drop_graphs(g);   // they hold the old arena's addresses
+    A.graphs.clear();
     FB2_CUDA_TRY(cudaMallocHost((void **)&A.h, need));
     FB2_CUDA_TRY(cudaMalloc((void **)&A.d, need));
     A.bytes = need;
     for (size_t i = 0; i < n; i++) {
-      int rc = reserve_scratch_for(view_of(lins[i]), device, std::max<size_t>(m, 64));
+      int rc = reserve_scratch_for(view_of(lins[i]), device, std::max<size_t>(max_m, 64));
       if (rc) return rc;
     }
   }
@@ -781,9 +817,9 @@ int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
     pin_in = pin_in && is_pinned(x_host[i]);
     pin_out = pin_out && is_pinned(y_host[i]);
   }
-  // Three streams, chunks of kChunk linears: the H2D copy of chunk c+1 and the D2H copy of chunk
-  // c-1 overlap the GEMMs of chunk c (two copy engines + compute).
-  constexpr size_t kChunk = 16;
+  // Three streams, chunks of kChunk linears (8: measured best of 4 / 8 / 16 on the 768-GEMM decode step): the H2D copy
+  // of chunk c+1 and the D2H copy of chunk c-1 overlap the GEMMs of chunk c (two copy engines + compute).
+  static const size_t kChunk = [] { const char *e = getenv("FB2_HOST_BATCH_CHUNK"); const int v = e ? atoi(e) : 0; return (size_t)(v > 0 ? v : 8); }();
   const size_t chunks = (n + kChunk - 1) / kChunk;
   if (A.ev_in.size() < chunks) {
     const size_t old = A.ev_in.size();
@@ -799,37 +835,112 @@ int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
     size_t xo = 0, yo = in_bytes;
     for (size_t i = 0; i < n; i++) {
       xoff[i] = xo; yoff[i] = yo;
-      xo += align256(m * lins[i]->w.k * 2);
-      yo += align256(m * lins[i]->w.n * 2);
+      xo += align256(ms[i] * lins[i]->w.k * 2);
+      yo += align256(ms[i] * lins[i]->w.n * 2);
+    }
+  }
+  // cached launch graphs of this (linears, m)
+  static const bool use_graphs = [] { const char *e = getenv("FB2_HOST_BATCH_GRAPHS"); return !(e && e[0] == '0'); }();
+  BatchGraphs *G = nullptr;
+  if (use_graphs) {
+    const uint64_t gen = g_handle_gen.load();
+    for (BatchGraphs &g : A.graphs)
+      if (g.lins.size() == n && std::equal(g.lins.begin(), g.lins.end(), lins) && std::equal(g.ms.begin(), g.ms.end(), ms)) { G = &g; break; }
+    if (G && (G->gen != gen || G->base != A.d)) {     // handles came or went: what the graphs point at may be gone
+      drop_graphs(*G);
+      G->gen = gen;
+      G->base = A.d;
+      G->no_graph = false;
+      G = nullptr;                                    // this call runs eagerly; the next one captures
+    } else if (!G) {
+      if (A.graphs.size() >= 16) {                    // keep the 16 most recently used keys
+        auto lru = std::min_element(A.graphs.begin(), A.graphs.end(),
+                                    [](const BatchGraphs &a, const BatchGraphs &b) { return a.last_use < b.last_use; });
+        drop_graphs(*lru);
+        A.graphs.erase(lru);
+      }
+      BatchGraphs g;
+      g.lins.assign(lins, lins + n);
+      g.ms.assign(ms, ms + n);
+      g.gen = gen;
+      g.base = A.d;
+      g.last_use = ++A.tick;
+      A.graphs.push_back(std::move(g));               // first sighting: eager (it also grows the scratch pools)
+    } else {
+      G->last_use = ++A.tick;
+      if (G->no_graph) G = nullptr;
+    }
+  }
+  if (G && G->chunk.empty()) {
+    // second call with this key: capture the GEMMs chunk by chunk
+    G->chunk.assign(chunks, nullptr);
+    G->chunk_launches.assign(chunks, 0);
+    for (size_t c = 0; c < chunks && !G->no_graph; c++) {
+      const size_t i0 = c * kChunk, i1 = std::min(n, i0 + kChunk);
+      const uint64_t l0 = g_launches.load();
+      if (cudaStreamBeginCapture(A.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); G->no_graph = true; break; }
+      int rc = FB2_OK;
+      for (size_t i = i0; i < i1 && rc == FB2_OK; i++)
+        rc = fb2_gptq_linear_forward(lins[i], A.stream, (const fb2_half *)(A.d + xoff[i]), (fb2_half *)(A.d + yoff[i]), ms[i]);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(A.stream, &graph);
+      if (rc != FB2_OK || ce != cudaSuccess || !graph ||
+          cudaGraphInstantiate(&G->chunk[c], graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        G->no_graph = true;
+      }
+      if (graph) cudaGraphDestroy(graph);
+      const uint64_t nl = g_launches.load() - l0;     // counted while capturing: nothing ran yet
+      g_launches.fetch_sub(nl);
+      G->chunk_launches[c] = (int)nl;
+    }
+    if (G->no_graph) {
+      drop_graphs(*G);
+      G = nullptr;
     }
   }
   for (size_t c = 0; c < chunks; c++) {
     const size_t i0 = c * kChunk, i1 = std::min(n, i0 + kChunk);
     for (size_t i = i0; i < i1; i++) {
-      const size_t xb = m * lins[i]->w.k * 2;
+      const size_t xb = ms[i] * lins[i]->w.k * 2;
+      if (xb == 0) continue;
       const void *src = x_host[i];
       if (!pin_in) { memcpy(A.h + xoff[i], x_host[i], xb); src = A.h + xoff[i]; }
       FB2_CUDA_TRY(cudaMemcpyAsync(A.d + xoff[i], src, xb, cudaMemcpyHostToDevice, A.copy_in));
     }
     FB2_CUDA_TRY(cudaEventRecord(A.ev_in[c], A.copy_in));
     FB2_CUDA_TRY(cudaStreamWaitEvent(A.stream, A.ev_in[c], 0));
-    for (size_t i = i0; i < i1; i++) {
-      int rc = fb2_gptq_linear_forward(lins[i], A.stream, (const fb2_half *)(A.d + xoff[i]),
-                                       (fb2_half *)(A.d + yoff[i]), m);
-      if (rc) return rc;
+    if (G) {
+      FB2_CUDA_TRY(cudaGraphLaunch(G->chunk[c], A.stream));
+      count_launch(G->chunk_launches[c]);
+    } else {
+      for (size_t i = i0; i < i1; i++) {
+        int rc = fb2_gptq_linear_forward(lins[i], A.stream, (const fb2_half *)(A.d + xoff[i]),
+                                         (fb2_half *)(A.d + yoff[i]), ms[i]);
+        if (rc) return rc;
+      }
     }
     FB2_CUDA_TRY(cudaEventRecord(A.ev_done[c], A.stream));
     FB2_CUDA_TRY(cudaStreamWaitEvent(A.copy_out, A.ev_done[c], 0));
     for (size_t i = i0; i < i1; i++) {
-      const size_t yb = m * lins[i]->w.n * 2;
+      const size_t yb = ms[i] * lins[i]->w.n * 2;
+      if (yb == 0) continue;
       void *dst = pin_out ? (void *)y_host[i] : (void *)(A.h + yoff[i]);
       FB2_CUDA_TRY(cudaMemcpyAsync(dst, A.d + yoff[i], yb, cudaMemcpyDeviceToHost, A.copy_out));
     }
   }
   FB2_CUDA_TRY(cudaStreamSynchronize(A.copy_out));
   if (!pin_out)
-    for (size_t i = 0; i < n; i++) memcpy(y_host[i], A.h + yoff[i], m * lins[i]->w.n * 2);
+    for (size_t i = 0; i < n; i++) memcpy(y_host[i], A.h + yoff[i], ms[i] * lins[i]->w.n * 2);
   return FB2_OK;
+}
+
+int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
+                                       const fb2_half *const *x_host, fb2_half *const *y_host,
+                                       size_t m) {
+  if (n == 0 || m == 0) return FB2_OK;
+  std::vector<size_t> ms(n, m);
+  return fb2_gptq_linear_forward_host_batch_m(lins, n, x_host, y_host, ms.data());
 }
 
 int fb2_gptq_linear_dequant_f32(const fb2_linear_t *lin, fb2_stream_t stream, float *w_nk) {

@@ -257,10 +257,12 @@ class HostBatch:
     """Pre-bound argument arrays for repeated forward_host_batch calls (keeps ctypes marshalling
     out of the timed region)."""
 
-    def __init__(self, linears: Sequence[_LinearBase], xs: Sequence[np.ndarray], outs: Sequence[np.ndarray], m: int):
+    def __init__(self, linears: Sequence[_LinearBase], xs: Sequence[np.ndarray], outs: Sequence[np.ndarray], m):
+        """m: rows of every entry, or one row count per entry (fb2_gptq_linear_forward_host_batch_m)."""
         n = len(linears)
         self._keep = (list(linears), list(xs), list(outs))
         self.n, self.m = n, m
+        self.ms = None if isinstance(m, int) else (C.c_size_t * n)(*[int(v) for v in m])
         self.hs = (C.c_void_p * n)(*[lin._h for lin in linears])
         self.xp = (C.c_void_p * n)(*[x.ctypes.data for x in xs])
         self.yp = (C.c_void_p * n)(*[y.ctypes.data for y in outs])
@@ -268,7 +270,10 @@ class HostBatch:
         self.d2h_bytes = sum(int(y.nbytes) for y in outs)
 
     def run(self) -> None:
-        check(lib().fb2_gptq_linear_forward_host_batch(self.hs, self.n, self.xp, self.yp, self.m))
+        if self.ms is None:
+            check(lib().fb2_gptq_linear_forward_host_batch(self.hs, self.n, self.xp, self.yp, self.m))
+        else:
+            check(lib().fb2_gptq_linear_forward_host_batch_m(self.hs, self.n, self.xp, self.yp, self.ms))
 
 
 # -------------------------------------------------------------------------------- stack

@@ -122,6 +122,11 @@ FB2_API int fb2_gptq_linear_forward_host(fb2_linear_t *lin, const fb2_half *x_ho
 FB2_API int fb2_gptq_linear_forward_host_batch(fb2_linear_t *const *lins, size_t n,
                                                const fb2_half *const *x_host,
                                                fb2_half *const *y_host, size_t m);
+/* The same with ms[i] rows for entry i (a decode step over requests of different batch sizes in ONE call: the copy
+ * pipeline fills and drains once).  Repeated calls with the same linears and rows replay cached launch graphs. */
+FB2_API int fb2_gptq_linear_forward_host_batch_m(fb2_linear_t *const *lins, size_t n,
+                                                 const fb2_half *const *x_host,
+                                                 fb2_half *const *y_host, const size_t *ms);
 
 /* Dequantise the stored weights back to the reference's [N, K] row-major matrix, in
  * ORIGINAL (disk) k order, exactly as cpu_dequant_gptq / dequantize_gptq_with_g_idx

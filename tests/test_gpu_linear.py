@@ -250,7 +250,7 @@ def test_host_batch_pageable_and_pinned(fb2, oracle, cuda, pinned):
     k, n, m = 512, 256, 5
     syn, gi = _make(oracle, k, n, 128, 0x51, "rand")
     lin = fb2.GptqLinear.from_raw(syn.qweight, syn.scales, syn.qzeros, gi, None, 4, 128, k, n)
-    lins = [lin] * 40
+    lins = [lin] * 40                              # (40 entries: chunks of 8)
     mk = (lambda a: torch.from_numpy(a).pin_memory().numpy()) if pinned else (lambda a: a)
     xs = [mk(oracle.f16_round(oracle.lcg_f32_array(100 + i, m * k, -1.0, 1.0)).reshape(m, k).astype(np.float16)) for i in range(40)]
     outs = [mk(np.zeros((m, n), dtype=np.float16)) for _ in range(40)]
@@ -258,3 +258,54 @@ def test_host_batch_pageable_and_pinned(fb2, oracle, cuda, pinned):
     for i in (0, 15, 16, 39):
         ref = lin.forward(torch.from_numpy(np.ascontiguousarray(xs[i])).cuda()).cpu().numpy()
         assert np.array_equal(outs[i].view(np.uint16), ref.view(np.uint16)), i
+
+
+def test_host_batch_cached_graphs(fb2, oracle, cuda):
+    """Repeated fb2_gptq_linear_forward_host_batch calls with the same linears and m replay cached per-chunk launch graphs
+    (first call eager, second captures, third replays): every call must equal the device-buffer forward bit for bit, with
+    new inputs each time, and a handle destroyed and re-created in between must invalidate the cache."""
+    torch = cuda
+    k, n, m = 512, 256, 3
+    syn, gi = _make(oracle, k, n, 128, 0x77, "rand")
+    mkl = lambda: fb2.GptqLinear.from_raw(syn.qweight, syn.scales, syn.qzeros, gi, None, 4, 128, k, n)
+    lins = [mkl() for _ in range(20)]
+    outs = [np.zeros((m, n), dtype=np.float16) for _ in range(20)]
+    def check(rep):
+        xs = [oracle.f16_round(oracle.lcg_f32_array(1000 * rep + i, m * k, -1.0, 1.0)).reshape(m, k).astype(np.float16) for i in range(20)]
+        for o in outs: o[...] = 0
+        fb2.forward_host_batch(lins, xs, m, outs)
+        for i in (0, 15, 16, 19):
+            ref = lins[i].forward(torch.from_numpy(np.ascontiguousarray(xs[i])).cuda()).cpu().numpy()
+            assert np.array_equal(outs[i].view(np.uint16), ref.view(np.uint16)), (rep, i)
+    for rep in range(4):
+        check(rep)
+    n0 = fb2.launch_count()
+    check(4)
+    assert fb2.launch_count() - n0 >= 20          # replayed graphs still count their kernels
+    lins[7] = None                                 # destroy one handle ...
+    import gc; gc.collect()
+    lins[7] = mkl()                                # ... and create another (possibly at the same address)
+    for rep in range(5, 8):
+        check(rep)
+
+
+def test_host_batch_rows_per_entry(fb2, oracle, cuda):
+    """fb2_gptq_linear_forward_host_batch_m: one call, a different row count per entry (zero rows = skipped), three times
+    (eager, capture, replay); bit-identical to the device-buffer forward."""
+    torch = cuda
+    k, n = 512, 256
+    syn, gi = _make(oracle, k, n, 128, 0x78, "rand")
+    lin = fb2.GptqLinear.from_raw(syn.qweight, syn.scales, syn.qzeros, gi, None, 4, 128, k, n)
+    ms = [1, 2, 0, 4, 8, 16, 32, 3, 5, 7, 9, 17, 33, 1, 64, 2, 6, 31]
+    lins = [lin] * len(ms)
+    for rep in range(3):
+        xs = [oracle.f16_round(oracle.lcg_f32_array(50 * rep + i, max(m, 1) * k, -1.0, 1.0)).reshape(max(m, 1), k).astype(np.float16) for i, m in enumerate(ms)]
+        outs = [np.zeros((max(m, 1), n), dtype=np.float16) for m in ms]
+        hb = fb2.HostBatch(lins, xs, outs, ms)
+        hb.run()
+        for i, m in enumerate(ms):
+            if m == 0:
+                assert not outs[i].any()
+                continue
+            ref = lin.forward(torch.from_numpy(np.ascontiguousarray(xs[i][:m])).cuda()).cpu().numpy()
+            assert np.array_equal(outs[i][:m].view(np.uint16), ref.view(np.uint16)), (rep, i, m)
