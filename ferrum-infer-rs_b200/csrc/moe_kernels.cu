@@ -289,17 +289,20 @@ route_align_small_kernel(const __half *__restrict__ logits, int32_t *__restrict_
     float sel_sum = 0.f, my_w = 0.f;
     int my_id = 0;
     for (int k = 0; k < top_k; k++) {                    // top_k <= 32 (route_align_small_supported)
-      float best = -INFINITY;
-      int best_i = 0x7fffffff;
+      // probabilities are >= 0 (removed ones -inf): their bit patterns order like signed integers, so the row maximum
+      // is ONE warp reduction (redux.sync) instead of five dependent shuffle pairs; the lowest index holding it wins
+      // (the reference's tie rule): lowest register first, lowest lane inside it
+      float lbest = pv[0];
 #pragma unroll
-      for (int j = 0; j < PER; j++)
-        if (pv[j] > best) { best = pv[j]; best_i = j * 32 + lane; }      // ascending i: the lowest index wins a tie
-      for (int o = 16; o; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+      for (int j = 1; j < PER; j++) lbest = fmaxf(lbest, pv[j]);
+      const float best = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(lbest)));
+      int best_i = 0;
+      bool found = false;
+#pragma unroll
+      for (int j = 0; j < PER; j++) {
+        const unsigned hit = __ballot_sync(0xffffffffu, pv[j] == best);
+        if (!found && hit) { best_i = j * 32 + (__ffs(hit) - 1); found = true; }
       }
-      if (best_i == 0x7fffffff) best_i = 0;
 #pragma unroll
       for (int j = 0; j < PER; j++)
         if (best_i == j * 32 + lane) pv[j] = -INFINITY;
