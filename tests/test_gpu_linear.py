@@ -209,7 +209,7 @@ def _sampled_forward_check(fb2, oracle, cuda, k, n, seed, act, ms, col_stride, r
                                       ("down_proj", 14336, 4096)])
 def test_llama_shapes_full_size(fb2, oracle, cuda, name, k, n):
     """BASELINE.json configs[1] at full size, act-order: every decode kernel class (M = 1: in-kernel gather; 8, 16:
-    gather launch + decode kernel; 32: the 64-row-block kernel) and the prefill class the bench times (M = 512)."""
+    gather launch + decode kernel, distributed owners from 16 rows; 32: its 32-row form) and the prefill class the bench times (M = 512)."""
     _sampled_forward_check(fb2, oracle, cuda, k, n, 0x77A0 + n, "rand", (1, 2, 8, 16, 32, 512), col_stride=max(1, n // 8 // 24))
 
 
@@ -309,3 +309,12 @@ def test_host_batch_rows_per_entry(fb2, oracle, cuda):
                 continue
             ref = lin.forward(torch.from_numpy(np.ascontiguousarray(xs[i][:m])).cuda()).cpu().numpy()
             assert np.array_equal(outs[i][:m].view(np.uint16), ref.view(np.uint16)), (rep, i, m)
+
+
+@pytest.mark.parametrize("k,n", [(512, 4096), (1792, 4096), (3584, 4096), (4096, 768), (4096, 3584), (4096, 1536),
+                                 (7168, 4096), (2048, 4096)])
+def test_tp_shard_shapes_decode_rows(fb2, oracle, cuda, k, n):
+    """The per-rank shapes of Llama-3.1-8B under TP 2 / 4 / 8 (row-parallel o / down: K / tp; column-parallel qkv /
+    gate_up: N / tp) at every decode row count the bench uses -- few units per tile and many contributors per split tile,
+    the corner the stream-K exchange variants (single owner, distributed owners, counter) have to survive."""
+    _sampled_forward_check(fb2, oracle, cuda, k, n, 0x7E57 + k + n, "rand", (1, 2, 4, 8, 16, 32), 4)
