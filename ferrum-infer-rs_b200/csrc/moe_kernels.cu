@@ -527,7 +527,8 @@ int launch_route_align_small(const __half *logits, int32_t *ids, float *wts, int
   // one warp per token; at least four warps for the alignment passes (and the act-order row gather CTAs)
   const int threads = gather ? kRouteAlignThreads : std::max(128, 32 * batch);
   auto go = [&](auto kernel) -> int {
-    if (smem > 48 * 1024) FB2_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (the kernel also holds ~12.3 KB of static shared memory: the opt-in is needed from 48 KB in total)
+    if (smem + 13 * 1024 > 48 * 1024) FB2_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return launch_pdl(kernel, dim3(gather ? 1 + batch : 1), dim3(threads), smem, stream, logits, ids, wts, sorted_ids,
                       block_ids, total_post_pad, batch, num_experts, top_k, norm, block_size, sorted_max, x, perm, xp, hidden);
   };

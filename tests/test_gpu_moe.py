@@ -236,11 +236,13 @@ def test_moe_ffn_qwen3_layer_shape(fb2, oracle, cuda, act, batches):
 
 
 @pytest.mark.parametrize("batch,E,top_k,norm", [(1, 60, 4, True), (7, 60, 4, False), (32, 128, 8, True), (32, 8, 1, True),
-                                                 (5, 40, 6, True), (33, 16, 2, True)])
+                                                 (5, 40, 6, True), (33, 16, 2, True), (3, 200, 8, True), (4, 320, 8, False),
+                                                 (2, 64, 40, True)])
 def test_moe_ffn_odd_router_shapes(fb2, oracle, cuda, batch, E, top_k, norm):
     """fb2_moe_ffn_forward across router shapes: expert counts that are not multiples of 32, top-1,
-    heavy collisions (32 tokens on 8 experts), and a batch just past the single-launch route+align
-    kernel's limit (33 -> the two-kernel path); against moe_forward_cpu (dispatch.rs:2208-2288)."""
+    heavy collisions (32 tokens on 8 experts), a batch just past the single-launch route+align kernel's limit
+    (33 -> the two-kernel path), more than 128 / 256 experts (the 8- and 32-registers-per-lane forms of that kernel) and
+    top_k > 32 (the two-kernel path again); against moe_forward_cpu (dispatch.rs:2208-2288)."""
     torch = cuda
     hidden, inter, g = 256, 128, 128
     gus = [oracle.make_synthetic(hidden, 2 * inter, g, 0x3100 + e, f16_scales=True) for e in range(E)]
