@@ -84,7 +84,7 @@ def test_cuda_desc_act_vs_cpu_reference(fb2, oracle, cuda):
     _check_forward(oracle, cuda, lin, syn, gi, 3, x=x)
 
 
-@pytest.mark.parametrize("m", [1, 2, 3, 4, 8, 15, 16, 17, 32, 33, 64, 65, 200])
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 8, 9, 15, 16, 17, 24, 31, 32, 33, 64, 65, 200])
 @pytest.mark.parametrize("act", [None, "rand"])
 def test_decode_and_small_prefill_rows(fb2, oracle, cuda, m, act):
     syn, gi = _make(oracle, 1024, 512, 128, 0xABC + m, act)
@@ -318,3 +318,23 @@ def test_tp_shard_shapes_decode_rows(fb2, oracle, cuda, k, n):
     gate_up: N / tp) at every decode row count the bench uses -- few units per tile and many contributors per split tile,
     the corner the stream-K exchange variants (single owner, distributed owners, counter) have to survive."""
     _sampled_forward_check(fb2, oracle, cuda, k, n, 0x7E57 + k + n, "rand", (1, 2, 4, 8, 16, 32), 4)
+
+
+@pytest.mark.parametrize("k,n", [(4096, 256), (8192, 128), (2048, 384), (14336, 128)])
+def test_many_contributors_per_tile(fb2, oracle, cuda, k, n):
+    """Deep, narrow layers: one to three tiles cut across 16+ CTAs -- more contributors than a split tile has row
+    vectors (several distributed owners idle), more than one polling round per owner -- at the row counts of every
+    exchange variant, twice (the flag-in-value slots must be back to empty after a launch)."""
+    syn, gi = _make(oracle, k, n, 128, 0x5EED + k + n, "rand")
+    lin = fb2.GptqLinear.from_raw(syn.qweight, syn.scales, syn.qzeros, gi, None, 4, 128, k, n)
+    w_ref = oracle.dequant_gptq(syn.qweight, syn.scales, syn.qzeros, gi, 4, 128, k, n)
+    for m in (1, 4, 8, 16, 32):
+        x = _x(oracle, m, k, seed=0xABC + m)
+        xd = cuda.from_numpy(x.astype(np.float16)).cuda()
+        y1 = lin.forward(xd)
+        y2 = lin.forward(xd)
+        cuda.cuda.synchronize()
+        assert cuda.equal(y1, y2), m
+        ref = oracle.gemm(x, w_ref, m, n, k, threads=8)
+        st = oracle.error_stats(y1.float().cpu().numpy(), ref)
+        assert st["rel"] < REL_TOL and st["nmse"] < NMSE_TOL, (lin.kernel_name(m), k, n, m, st)
