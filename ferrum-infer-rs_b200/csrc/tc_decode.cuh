@@ -30,7 +30,7 @@
 #pragma once
 
 #ifndef FB2_QUARTER_MIN_R
-#define FB2_QUARTER_MIN_R 8
+#define FB2_QUARTER_MIN_R 32
 #endif
 namespace dk {
 
