@@ -1,4 +1,4 @@
-// tc_decode.cuh -- the decode-batch (<= 16 rows per block) form of the tensor-core W4A16 kernel.  Included by
+// tc_decode.cuh -- the decode-batch (<= 32 rows per block) form of the tensor-core W4A16 kernel.  Included by
 // tc_gemm.cu (same translation unit: it shares TcParams, the stream-K bookkeeping and the launch helpers).
 //
 // What differs from tc_body (tc_gemm.cu):
@@ -23,7 +23,11 @@
 //     instruction count bought 13 %).
 //   * The accumulators live in registers, so the MMA warp knows nothing about tiles or segments, and the epilogue
 //     starts from registers: the two groups swap the rows the other one finishes through shared memory, then run
-//     the whole-tile / flag-in-value / counter exchange of tc_body.
+//     the whole-tile / flag-in-value / counter exchange of tc_body -- with 16+ rows and 4+ contributors the rows of a
+//     split tile are finished by all contributors but the last, a share each (one polling round instead of several).
+//   * REGISTERS WHERE THE WORK IS.  The producer / MMA warps (one warpgroup) hand registers to the two dequant
+//     warpgroups (setmaxnreg 48 / 96); the running sums are never indexed at run time, so nothing of the unit loop
+//     lives in local memory (which does not fit the L1 this kernel leaves).
 // Row sources: dense rows through the tensor map (DK_DENSE); dense rows of an act-order layer gathered inside the
 // kernel (DK_GATHER); moe_align_block_size blocks of a stacked expert weight (DK_ROUTED, block <= 16), optionally with
 // the gate | up accumulator pair and the SwiGLU epilogue (kSilu).
