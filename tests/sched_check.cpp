@@ -5,6 +5,9 @@
 //   3. a CTA's segments tile its range, never cross an output tile, and name the right (block, tile, r);
 //   4. the contributors of a split tile are the consecutive CTAs c_first .. c_last; the tile is the LAST segment of
 //      c_first's range and the FIRST segment (at_start) of every other contributor's -- the ownership rule of the fix-up;
+//      4b. (distributed owners, tc_decode.cuh) the tile is also the LAST segment of every contributor but c_last, so an
+//      owner never waits in the middle of its range; and a CTA holds at most one piece as "last contributor" and at most one
+//      other split piece -- one per slot area;
 //   5. in whole-tile mode no tile is split; with the tile-aligned grid no CTA holds pieces of two tiles;
 //   6. every product stays below 2^31 when units * grid does (the 32-bit arithmetic the kernel uses).
 #include <cstdint>
@@ -101,6 +104,7 @@ static void check_plan(int row_blocks, int n_tiles, int upt, int slots, bool rou
       CHECK(start[c] <= u && u < start[c + 1], "cta_of_unit(%u) = %d", u, c);
     }
     // (4): ownership of split tiles
+    std::vector<int> as_last, as_other;
     for (size_t i = 0; i < segs.size(); i++) {
       const SegRec &s = segs[i];
       if (s.r0 == 0 && s.r1 == upt) continue;                 // this CTA covered the whole tile
@@ -113,6 +117,10 @@ static void check_plan(int row_blocks, int n_tiles, int upt, int slots, bool rou
       else CHECK(s.at_start, "contributor's piece is not the first segment of its range");
       if (s.cta == c_first) CHECK(s.r0 == 0, "owner does not start the tile");
       if (s.cta == c_last) CHECK(s.r1 == upt, "last contributor does not end the tile");
+      if (s.cta != c_last) CHECK(s.last, "a contributor other than the last would wait in the middle of its range");   // 4b
+      if ((int)as_last.size() <= s.cta) { as_last.resize(s.cta + 1, 0); as_other.resize(s.cta + 1, 0); }
+      if (s.cta == c_last) as_last[s.cta]++; else as_other[s.cta]++;
+      CHECK(as_last[s.cta] <= 1 && as_other[s.cta] <= 1, "CTA %d needs more than two slot areas", s.cta);
     }
   }
 }
