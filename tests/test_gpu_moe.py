@@ -260,3 +260,27 @@ def test_moe_ffn_odd_router_shapes(fb2, oracle, cuda, batch, E, top_k, norm):
     ref = oracle.moe_forward_cpu(x, batch, hidden, inter, top_k, ids, w, guw, dnw)
     st = oracle.error_stats(out.float().cpu().numpy(), ref)
     assert st["rel"] < 1e-2 and st["nmse"] < 1e-5, st
+
+
+@pytest.mark.parametrize("batch,E,top_k", [(8, 128, 8), (3, 200, 8), (32, 16, 4)])
+def test_moe_ffn_router_ties(fb2, oracle, cuda, batch, E, top_k):
+    """Logits on four levels only: almost every top-k decision is a tie, which the reference breaks towards the lower
+    expert index (router.rs:160-183).  The single-launch route + align kernel picks the row maximum by a warp reduction and
+    the lowest index holding it; a different tie rule would route tokens to other experts and miss the oracle by far."""
+    torch = cuda
+    hidden, inter, g = 256, 128, 128
+    gus = [oracle.make_synthetic(hidden, 2 * inter, g, 0x5100 + e, f16_scales=True) for e in range(E)]
+    dns = [oracle.make_synthetic(inter, hidden, g, 0x6200 + e, f16_scales=True) for e in range(E)]
+    mk = lambda parts, k, n: fb2.GptqExpertStack.load_gptq_stacked([p.qweight for p in parts], [p.scales for p in parts],
+                                                                   [p.qzeros for p in parts], None, 4, g, k, n)
+    guw = np.stack([oracle.dequant_gptq(p.qweight, p.scales, p.qzeros, None, 4, g, hidden, 2 * inter) for p in gus])
+    dnw = np.stack([oracle.dequant_gptq(p.qweight, p.scales, p.qzeros, None, 4, g, inter, hidden) for p in dns])
+    x = oracle.f16_round(oracle.lcg_f32_array(31, batch * hidden, -1.0, 1.0)).reshape(batch, hidden)
+    lg = np.floor(oracle.lcg_f32_array(32, batch * E, 0.0, 3.999)).reshape(batch, E).astype(np.float32) * 0.5 - 1.0
+    ffn = fb2.moe.MoeFfn(mk(gus, hidden, 2 * inter), mk(dns, inter, hidden), top_k, True, max_batch=batch)
+    out = ffn.forward(torch.from_numpy(x.astype(np.float16)).cuda(), torch.from_numpy(lg.astype(np.float16)).cuda())
+    torch.cuda.synchronize()
+    ids, w = oracle.route(lg, batch, E, top_k, True)
+    ref = oracle.moe_forward_cpu(x, batch, hidden, inter, top_k, ids, w, guw, dnw)
+    st = oracle.error_stats(out.float().cpu().numpy(), ref)
+    assert st["rel"] < 1e-2 and st["nmse"] < 1e-5, st
